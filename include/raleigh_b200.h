@@ -1,0 +1,183 @@
+/*
+ * raleigh_b200 -- C ABI of the B200 (sm_100a) block-vector algebra library.
+ *
+ * This is the drop-in boundary for the hot path of RALEIGH's block
+ * Jacobi-conjugated-gradient eigensolver: the abstract `Vectors` algebra, the
+ * dense `Matrix` operator and the sparse symmetric operator.  Each entry point
+ * replaces one vendor-library call site of the reference (cuBLAS / cuSOLVER in
+ * raleigh/algebra/dense_cublas.py, MKL in raleigh/algebra/mkl_wrap.py); the
+ * reference line it stands in for is cited next to every declaration.
+ *
+ * Conventions
+ *   - plain C types only; every function returns int: 0 = ok, >0 = cudaError_t,
+ *     <0 = RL_E_* argument error.  rl_error_string() decodes both.
+ *   - block vectors are VECTOR-MAJOR: vector j, component r lives at
+ *     base[j*ld + r] (the reference's C-ordered (nvec, n) array, ld >= n).
+ *     "m" counts vectors of `self`/output, "k" vectors of `other`/input,
+ *     "n" is the vector dimension (rows of the eigenproblem).
+ *   - all pointers are DEVICE pointers unless the name ends in _h (host).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Work is enqueued asynchronously; *_h entry points that return data to
+ *     the host synchronise the stream before returning.
+ *   - dtype: RL_F32 / RL_F64 (complex types of the reference are not built).
+ */
+#ifndef RALEIGH_B200_H
+#define RALEIGH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { RL_F32 = 0, RL_F64 = 1 };
+
+enum {
+    RL_E_DTYPE = -1,      /* unsupported dtype code */
+    RL_E_ARG = -2,        /* negative size / null pointer / bad stride */
+    RL_E_WORKSPACE = -3,  /* workspace too small */
+    RL_E_ALIAS = -4,      /* output aliases an input where that is not allowed */
+    RL_E_NOTCONV = -5     /* small dense eigensolver did not converge */
+};
+
+/* ---- library / device -------------------------------------------------- */
+int rl_version(void);
+const char* rl_error_string(int rc);
+/* cuda_wrap.py:139-141 (getDeviceCount / getDeviceProperties / synchronize) */
+int rl_device_count(int* count);
+int rl_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
+                   size_t* l2_bytes, size_t* total_mem);
+int rl_sync_device(void);
+int rl_sync_stream(void* stream);
+/* counts kernels this library has launched since load (bench.py gpu_launches) */
+int64_t rl_launch_count(void);
+
+/* ---- raw memory (cuda_wrap.py:142-153: malloc/free/memset/memcpy/memcpy2D;
+ *      size_t sizes instead of the reference's c_int) ---------------------- */
+int rl_malloc(void** ptr, size_t bytes);
+int rl_free(void* ptr);
+int rl_memset(void* ptr, int value, size_t bytes, void* stream);
+int rl_h2d(void* dst, const void* src_h, size_t bytes, void* stream);
+int rl_d2h(void* dst_h, const void* src, size_t bytes, void* stream);
+/* strided host<->device block copies; widths/pitches in BYTES */
+int rl_h2d_2d(void* dst, size_t dpitch, const void* src_h, size_t spitch,
+              size_t width, size_t height, void* stream);
+int rl_d2h_2d(void* dst_h, size_t dpitch, const void* src, size_t spitch,
+              size_t width, size_t height, void* stream);
+
+/* ---- Vectors: data movement --------------------------------------------- */
+/* Vectors.copy(other)  dense_cublas.py:133-145  (cublas?copy over m*n) */
+int rl_copy(int dtype, void* dst, int64_t ld_dst, const void* src, int64_t ld_src,
+            int64_t m, int64_t n, void* stream);
+/* Vectors.copy(other, ind)  dense_cublas.py:146-153 (one cublas?copy per index):
+ * dst[t] <- src_all[ind_h[t]], t < count; ind_h are absolute vector indices. */
+int rl_gather(int dtype, void* dst, int64_t ld_dst, const void* src_all,
+              int64_t ld_src, const int64_t* ind_h, int64_t count, int64_t n,
+              void* stream);
+/* Vectors.fill_random device mode (reference: host numpy.random.rand + H2D,
+ * dense_cublas.py:119-131).  Counter-based: element (j0+j, r0+r) depends only on
+ * (seed, global vector index, global row index), so shards reproduce the
+ * unsharded fill.  Values uniform in (-1, 1). */
+int rl_fill_uniform(int dtype, void* x, int64_t ld, int64_t m, int64_t n,
+                    uint64_t seed, int64_t j0, int64_t r0, void* stream);
+
+/* ---- Vectors: BLAS-1 like ---------------------------------------------- */
+/* Vectors.add(other, s) scalar  dense_cublas.py:311-316 (cublas?axpy) : Y += alpha*X */
+int rl_axpy(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx,
+            int64_t m, int64_t n, double alpha, void* stream);
+/* Vectors.add(other, s[]) dense_cublas.py:343-350 (m cublas?axpy calls): Y[i] += s[i]*X[i] */
+int rl_axpy_diag(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx,
+                 int64_t m, int64_t n, const void* s, void* stream);
+int rl_axpy_diag_h(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx,
+                   int64_t m, int64_t n, const void* s_h, void* stream);
+/* Vectors.scale(s, multiply) dense_cublas.py:155-172 (m cublas?scal calls):
+ * multiply != 0: Y[i] *= s[i]; else Y[i] /= s[i] where s[i] != 0 */
+int rl_scale(int dtype, void* y, int64_t ldy, int64_t m, int64_t n,
+             const void* s, int multiply, void* stream);
+int rl_scale_h(int dtype, void* y, int64_t ldy, int64_t m, int64_t n,
+               const void* s_h, int multiply, void* stream);
+/* Vectors.dots(other) dense_cublas.py:222-243 (m cublas?dot calls):
+ * w[i] = sum_r O[i,r]*S[i,r].  Deterministic two-phase reduction. */
+size_t rl_dots_ws_bytes(int dtype, int64_t m, int64_t n);
+int rl_dots(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo,
+            int64_t m, int64_t n, void* w, void* ws, size_t ws_bytes, void* stream);
+int rl_dots_h(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo,
+              int64_t m, int64_t n, void* w_h, void* stream);
+/* Vectors.dots(other, transp=True) dense_cublas.py:175-221 (gemmBatched of n 1x1):
+ * w[r] = sum_i O[i,r]*S[i,r], length n */
+int rl_dots_t(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo,
+              int64_t m, int64_t n, void* w, void* stream);
+/* Jacobi preconditioner through Operator.apply (sparse_mkl.py:143-154):
+ * Y[i,r] = X[i,r]*d[r]  (d = 1/diag(A), length n) */
+int rl_diag_mul(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx,
+                int64_t m, int64_t n, const void* d, void* stream);
+
+/* ---- Vectors: tall-skinny BLAS-3 like ------------------------------------ */
+/* Vectors.dot(other) dense_cublas.py:245-269 (cublas?gemm T,N + D2H):
+ * G[i*m + j] = sum_r O[i,r]*S[j,r]  -- (k, m) row-major, exactly the ndarray
+ * the reference returns.  Deterministic: per-CTA partials in fixed slots of
+ * `ws`, then a fixed-order tree; no floating-point atomics. */
+size_t rl_gram_ws_bytes(int dtype, int64_t m, int64_t k, int64_t n);
+int rl_gram(int dtype, const void* s, int64_t lds, int64_t m, const void* o,
+            int64_t ldo, int64_t k, int64_t n, void* g, void* ws, size_t ws_bytes,
+            void* stream);
+int rl_gram_h(int dtype, const void* s, int64_t lds, int64_t m, const void* o,
+              int64_t ldo, int64_t k, int64_t n, void* g_h, void* stream);
+/* Same product with fp64 accumulation and an fp64 (k, m) result whatever the
+ * data dtype: the Gram matrix the on-device SVD / orthonormalisation factorises
+ * (squaring the condition number in fp32 would lose the small singular values). */
+size_t rl_gram_acc64_ws_bytes(int dtype, int64_t m, int64_t k, int64_t n);
+int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* o,
+                  int64_t ldo, int64_t k, int64_t n, double* g, void* ws,
+                  size_t ws_bytes, void* stream);
+/* test hook: non-zero forces the FMA-pipe Gram kernel for fp64 (A/B runs) */
+void rl_debug_set_gram_simt(int on);
+/* Vectors.multiply(q, out) dense_cublas.py:271-299 (gemm, beta=0) and
+ * Vectors.add(other, s, q) dense_cublas.py:317-342 (gemm, beta=1):
+ * Out[j,:] = beta*Out[j,:] + alpha * sum_{i<k} Q[i*q_rs + j*q_cs] * X[i,:], j < m.
+ * Q strides are in elements (C-, F-ordered or strided views all map here).
+ * Out must not overlap X. */
+int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x,
+              int64_t ldx, int64_t k, const void* q, int64_t q_rs, int64_t q_cs,
+              double alpha, double beta, int64_t n, void* stream);
+int rl_update_h(int dtype, void* out, int64_t ldo, int64_t m, const void* x,
+                int64_t ldx, int64_t k, const void* q_h, int64_t q_rs, int64_t q_cs,
+                double alpha, double beta, int64_t n, void* stream);
+
+/* ---- dense Matrix operator ---------------------------------------------- */
+/* Matrix.apply(x, y, transp) dense_cublas.py:732-776 (cublas?gemm):
+ * A is (M, N) row-major with leading dimension lda;
+ *   transp == 0: Y[v,i] = sum_j X[v,j]*A[i,j]   (x dim N -> y dim M)
+ *   transp != 0: Y[v,j] = sum_i X[v,i]*A[i,j]   (x dim M -> y dim N)
+ * Y = alpha*result + beta*Y.  The fp32 path uses tcgen05 tensor cores with a
+ * 3xTF32 split when the shape allows, else an fp32 FMA kernel. */
+int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N,
+                   const void* x, int64_t ldx, void* y, int64_t ldy, int64_t k,
+                   int transp, double alpha, double beta, void* stream);
+
+/* ---- sparse symmetric operator ------------------------------------------- */
+/* SparseSymmetricMatrix.apply sparse_mkl.py:42-48 -> mkl_?csrmm mkl_wrap.py:274-276
+ * (and mkl_?csrsymv :261-262 for m == 1).  The device holds the FULL symmetric
+ * matrix as 0-based CSR (indptr int64, indices int32).
+ * Y[v, r] = sum_{p in row r} val[p] * X[v, col[p]],  rows [row0, row0+nrows) of
+ * the operator write Y[v, 0..nrows) (row-sharded use: X is the gathered vector
+ * of dimension ncols). */
+int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr,
+                const int32_t* indices, const void* values, const void* x, int64_t ldx,
+                void* y, int64_t ldy, int64_t m, void* stream);
+
+/* ---- small dense algebra on device (no host LAPACK) ----------------------- */
+/* Symmetric eigen-decomposition of the (p, p) row-major matrix `a` (fp64) by
+ * cyclic Jacobi rotations: on return w[0..p) ascending eigenvalues and a holds
+ * the eigenvectors as COLUMNS (a[i*p + j] = component i of eigenvector j).
+ * Used by Vectors.svd (dense_cublas.py:537-591 cusolverDn?gesvd) via the Gram
+ * route and by the device Rayleigh-Ritz.  ws >= rl_syevj_ws_bytes(p). */
+size_t rl_syevj_ws_bytes(int64_t p);
+int rl_syevj(double* a, int64_t p, double* w, void* ws, size_t ws_bytes,
+             int* sweeps_out_h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RALEIGH_B200_H */

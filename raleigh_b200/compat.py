@@ -1,0 +1,84 @@
+"""Make the UNMODIFIED reference package run on this backend.
+
+The reference's interfaces reach their algebra through hard-coded module
+imports (partial_hevp.py:14-17 -> dense_cblas / sparse_mkl; dense_matrix.py:17-18
+-> cuda_wrap / dense_cublas).  `install()` registers this package's modules under
+those names *before* the interfaces are imported, so
+
+    import raleigh_b200; raleigh_b200.install()
+    from raleigh.interfaces.pca import pca                 # arch='gpu!'
+    from raleigh.interfaces.partial_hevp import partial_hevp
+
+run verbatim on the B200 kernels.  It also applies the SciPy >= 1.14 shim the
+reference needs on any backend: `scipy.linalg.eigh(..., turbo=False)`
+(solver.py:578,822,899,1470) no longer accepts `turbo`.
+"""
+import importlib
+import os
+import sys
+
+_ALIASES = {
+    'dense_cublas': 'raleigh_b200.vectors',
+    'dense_cblas': 'raleigh_b200.vectors',
+    'cuda_wrap': 'raleigh_b200.cuda',
+    'sparse_mkl': 'raleigh_b200.sparse',
+}
+
+
+def find_reference():
+    """Directory that contains the reference's `raleigh` package, or None.
+    Order: already importable, $RALEIGH_REFERENCE, <repo>/baseline/_ref."""
+    try:
+        spec = importlib.util.find_spec('raleigh')
+        if spec is not None and spec.submodule_search_locations:
+            return os.path.dirname(list(spec.submodule_search_locations)[0])
+    except (ImportError, ValueError):
+        pass
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get('RALEIGH_REFERENCE'), os.path.join(here, 'baseline', '_ref')):
+        if cand and os.path.isdir(os.path.join(cand, 'raleigh')):
+            return cand
+    return None
+
+
+class _SlaProxy:
+    """scipy.linalg with the removed `turbo` keyword of eigh() accepted and dropped."""
+
+    def __init__(self, sla):
+        self._sla = sla
+
+    def __getattr__(self, name):
+        return getattr(self._sla, name)
+
+    def eigh(self, *args, turbo=None, **kwargs):
+        return self._sla.eigh(*args, **kwargs)
+
+
+def shim_scipy():
+    import scipy.linalg as sla
+    import raleigh.core.solver as rsolver
+    if not isinstance(rsolver.sla, _SlaProxy):
+        rsolver.sla = _SlaProxy(sla)
+
+
+def install(reference_path=None, sparse=True, dense=True):
+    """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.
+    Raises ImportError if the reference package cannot be found."""
+    path = reference_path or find_reference()
+    if path is None:
+        raise ImportError('reference package `raleigh` not found (looked at sys.path, '
+                          '$RALEIGH_REFERENCE, baseline/_ref)')
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import raleigh
+    import raleigh.algebra as algebra
+    for name, target in _ALIASES.items():
+        if name == 'sparse_mkl' and not sparse:
+            continue
+        if name != 'sparse_mkl' and not dense:
+            continue
+        mod = importlib.import_module(target)
+        sys.modules['raleigh.algebra.' + name] = mod
+        setattr(algebra, name, mod)
+    shim_scipy()
+    return raleigh

@@ -1,0 +1,70 @@
+// Shared helpers for the raleigh_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/raleigh_b200.h"
+
+#define RL_SM_COUNT_DEFAULT 148
+
+namespace rl {
+
+extern int64_t g_launches;          // kernels launched by this library (api.cu)
+int sm_count();                     // cached cudaDevAttrMultiProcessorCount
+
+inline int check_launch() {
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+#define RL_CUDA(expr)                         \
+    do {                                      \
+        cudaError_t _e = (expr);              \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T> struct Vec128;          // 16-byte vector of T
+template <> struct Vec128<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec128<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ bool aligned16(const void* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+inline bool host_aligned16(const void* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// streaming (read-once) 128-bit load: keep it out of L1
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Library-owned scratch: a pinned host ring + a device ring used by the *_h
+// entry points to move small coefficient / result arrays (api.cu).
+struct Staging {
+    void* pinned = nullptr;   // cudaHostAlloc
+    void* dev = nullptr;      // cudaMalloc
+    size_t bytes = 0;
+};
+int staging_acquire(size_t bytes, void** pinned, void** dev);   // grows on demand
+int scratch_acquire(size_t bytes, void** dev);                  // second device scratch (workspaces)
+
+}  // namespace rl

@@ -1,0 +1,391 @@
+// Tall-skinny Gram product  G[i,j] = sum_r O[i,r] * S[j,r]   (Vectors.dot,
+// dense_cublas.py:245-269).  O is (k, n), S is (m, n), both vector-major, so the
+// reduction index r is the contiguous one for both operands.
+//
+// Algorithmic traffic: (m + k) * n * w bytes in, k*m*w out  -> HBM-bound for
+// m,k <= ~32 in fp64 (AI = m*k/(4(m+k)) flop/B), FP64-pipe-bound beyond.
+//
+// fp64 path: warp-level DMMA (mma.sync.m8n8k4.f64).  A warp owns an
+// (8*NI) x (8*NJ) tile of G and a contiguous range of rows; per step of 16 rows
+// each lane issues NI+NJ pairs of 128-bit loads straight from global memory
+// (the fragment layout of m8n8k4 lets lane (g, c) read 4 consecutive rows
+// 4c..4c+3 of vector g -- a full 128-byte line per vector per warp) and then
+// NI*NJ*4 DMMAs.  No shared-memory staging is needed: every loaded element is
+// used NI (or NJ) times from registers.
+//
+// fp32 path (and fp32-data/fp64-accumulate used by svd()): SIMT, lane = row,
+// TI x TJ register tile, warp-shuffle reduction at the end.
+//
+// Determinism: each (chunk, tile) CTA writes its partial tile into a fixed slot
+// of the workspace; a second kernel adds the chunk partials in a fixed order
+// (strided per lane + xor-shuffle tree).  No floating-point atomics anywhere.
+#include "common.cuh"
+
+namespace rl {
+
+constexpr int GRAM_WARPS = 4;
+constexpr int GRAM_THREADS = GRAM_WARPS * 32;
+
+struct GramPlan {
+    int ni, nj;          // 8-wide fragments per warp tile along k (other) and m (self)
+    int tiles_i, tiles_j;
+    int chunks;          // row chunks (CTAs along the reduction)
+    int64_t rows_per_warp;
+};
+
+static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
+    GramPlan p;
+    auto frag = [](int64_t v) { return v <= 8 ? 1 : v <= 16 ? 2 : 4; };
+    p.ni = frag(k);
+    p.nj = frag(m);
+    p.tiles_i = (int)((k + 8 * p.ni - 1) / (8 * p.ni));
+    p.tiles_j = (int)((m + 8 * p.nj - 1) / (8 * p.nj));
+    int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
+    // enough CTAs for ~4 per SM, but at least 64 rows (4 steps) per warp
+    int64_t want = ((int64_t)sm_count() * 4 + tiles - 1) / tiles;
+    int64_t maxc = (n + GRAM_WARPS * 64 - 1) / (GRAM_WARPS * 64);
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    int64_t rows_per_cta = (n + want - 1) / want;
+    int64_t rpw = (rows_per_cta + GRAM_WARPS - 1) / GRAM_WARPS;
+    rpw = (rpw + 15) / 16 * 16;
+    p.rows_per_warp = rpw;
+    p.chunks = (int)((n + rpw * GRAM_WARPS - 1) / (rpw * GRAM_WARPS));
+    return p;
+}
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Loads 4 consecutive rows r..r+3 of one vector for the current lane.
+// ALIGNED: two 128-bit loads, caller guarantees r+3 < n and 16-byte alignment.
+template <bool ALIGNED>
+__device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, int64_t n, bool active,
+                                      double (&v)[4]) {
+    if (ALIGNED) {
+        if (active) {
+            double2 a = ldg_stream(reinterpret_cast<const double2*>(p + r));
+            double2 b = ldg_stream(reinterpret_cast<const double2*>(p + r) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+            v[0] = v[1] = v[2] = v[3] = 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = (active && r + t < n) ? __ldg(p + r + t) : 0.0;
+    }
+}
+
+template <int NI, int NJ>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double* __restrict__ O, int64_t ldo,
+                 int k, int64_t n, int64_t rows_per_warp, int fast, double* __restrict__ part) {
+    __shared__ double red[GRAM_WARPS][NI * NJ * 64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ);
+    const int chunk = blockIdx.x;
+
+    const double* po[NI];
+    const double* ps[NJ];
+    bool ai[NI], aj[NJ];
+#pragma unroll
+    for (int t = 0; t < NI; ++t) { int i = i0 + 8 * t + g; ai[t] = i < k; po[t] = O + (int64_t)(ai[t] ? i : 0) * ldo; }
+#pragma unroll
+    for (int t = 0; t < NJ; ++t) { int j = j0 + 8 * t + g; aj[t] = j < m; ps[t] = S + (int64_t)(aj[t] ? j : 0) * lds; }
+
+    double acc[NI][NJ][2];
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    int64_t r_begin = ((int64_t)chunk * GRAM_WARPS + warp) * rows_per_warp;
+    int64_t r_end = r_begin + rows_per_warp < n ? r_begin + rows_per_warp : n;
+    int64_t r = r_begin;
+    if (fast) {
+        // full 16-row steps with 128-bit loads
+        for (; r + 16 <= r_end; r += 16) {
+            double fa[NI][4], fb[NJ][4];
+#pragma unroll
+            for (int t = 0; t < NI; ++t) load4<true>(po[t], r + 4 * c, n, ai[t], fa[t]);
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) load4<true>(ps[t], r + 4 * c, n, aj[t], fb[t]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int a = 0; a < NI; ++a)
+#pragma unroll
+                    for (int b = 0; b < NJ; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a][s], fb[b][s]);
+        }
+    }
+    for (; r < r_end; r += 16) {   // ragged / unaligned steps
+        double fa[NI][4], fb[NJ][4];
+#pragma unroll
+        for (int t = 0; t < NI; ++t) load4<false>(po[t], r + 4 * c, r_end, ai[t], fa[t]);
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) load4<false>(ps[t], r + 4 * c, r_end, aj[t], fb[t]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int a = 0; a < NI; ++a)
+#pragma unroll
+                for (int b = 0; b < NJ; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a][s], fb[b][s]);
+    }
+
+    // C fragment: lane (g, c) holds rows g, cols 2c, 2c+1 of each 8x8 block
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ; ++b) {
+            red[warp][(a * NJ + b) * 64 + g * 8 + 2 * c] = acc[a][b][0];
+            red[warp][(a * NJ + b) * 64 + g * 8 + 2 * c + 1] = acc[a][b][1];
+        }
+    __syncthreads();
+    double* out = part + (int64_t)chunk * k * m;
+    for (int e = threadIdx.x; e < NI * NJ * 64; e += GRAM_THREADS) {
+        double v = red[0][e];
+#pragma unroll
+        for (int w = 1; w < GRAM_WARPS; ++w) v += red[w][e];
+        int blk = e >> 6, a = blk / NJ, b = blk % NJ;
+        int i = i0 + 8 * a + ((e & 63) >> 3), j = j0 + 8 * b + (e & 7);
+        if (i < k && j < m) out[(int64_t)i * m + j] = v;
+    }
+}
+
+// ---- SIMT path (fp32, or fp32 data with fp64 accumulation) ---------------------
+// lane = row; the warp owns a TI x TJ tile of G; per step every lane reads VR
+// consecutive rows of TI + TJ vectors with one 128-bit load each.
+template <typename T, typename TA, int TI, int TJ>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_simt_kernel(const T* __restrict__ S, int64_t lds, int m, const T* __restrict__ O, int64_t ldo, int k,
+                 int64_t n, int64_t rows_per_warp, int fast, TA* __restrict__ part) {
+    constexpr int V = Vec128<T>::N;
+    using VT = typename Vec128<T>::type;
+    __shared__ TA red[GRAM_WARPS][TI * TJ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.z * TI, j0 = blockIdx.y * TJ;
+    const int chunk = blockIdx.x;
+    TA acc[TI][TJ];
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+#pragma unroll
+        for (int b = 0; b < TJ; ++b) acc[a][b] = TA(0);
+
+    int64_t r_begin = ((int64_t)chunk * GRAM_WARPS + warp) * rows_per_warp;
+    int64_t r_end = r_begin + rows_per_warp < n ? r_begin + rows_per_warp : n;
+    int64_t r = r_begin;
+    if (fast) {
+        for (; r + 32 * V <= r_end; r += 32 * V) {
+            VT fa[TI], fb[TJ];
+#pragma unroll
+            for (int a = 0; a < TI; ++a) {
+                int i = i0 + a;
+                fa[a] = ldg_stream(reinterpret_cast<const VT*>(O + (int64_t)(i < k ? i : 0) * ldo + r) + lane);
+            }
+#pragma unroll
+            for (int b = 0; b < TJ; ++b) {
+                int j = j0 + b;
+                fb[b] = ldg_stream(reinterpret_cast<const VT*>(S + (int64_t)(j < m ? j : 0) * lds + r) + lane);
+            }
+#pragma unroll
+            for (int a = 0; a < TI; ++a)
+#pragma unroll
+                for (int b = 0; b < TJ; ++b) {
+                    const T* ea = reinterpret_cast<const T*>(&fa[a]);
+                    const T* eb = reinterpret_cast<const T*>(&fb[b]);
+#pragma unroll
+                    for (int t = 0; t < V; ++t) acc[a][b] = fma((TA)ea[t], (TA)eb[t], acc[a][b]);
+                }
+        }
+    }
+    for (int64_t rr = r + lane; rr < r_end; rr += 32) {
+        T fa[TI], fb[TJ];
+#pragma unroll
+        for (int a = 0; a < TI; ++a) { int i = i0 + a; fa[a] = i < k ? __ldg(O + (int64_t)i * ldo + rr) : T(0); }
+#pragma unroll
+        for (int b = 0; b < TJ; ++b) { int j = j0 + b; fb[b] = j < m ? __ldg(S + (int64_t)j * lds + rr) : T(0); }
+#pragma unroll
+        for (int a = 0; a < TI; ++a)
+#pragma unroll
+            for (int b = 0; b < TJ; ++b) acc[a][b] = fma((TA)fa[a], (TA)fb[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+#pragma unroll
+        for (int b = 0; b < TJ; ++b) {
+            TA v = warp_sum(acc[a][b]);
+            if (lane == 0) red[warp][a * TJ + b] = v;
+        }
+    __syncthreads();
+    TA* out = part + (int64_t)chunk * k * m;
+    for (int e = threadIdx.x; e < TI * TJ; e += GRAM_THREADS) {
+        TA v = red[0][e];
+#pragma unroll
+        for (int w = 1; w < GRAM_WARPS; ++w) v += red[w][e];
+        int i = i0 + e / TJ, j = j0 + e % TJ;
+        if (i < k && j < m) out[(int64_t)i * m + j] = v;
+    }
+}
+
+// ---- second phase: fixed-order sum over the chunk partials ------------------------
+// 8 lanes per output entry: lane l adds chunks l, l+8, ... then a 3-level xor tree.
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const TA* __restrict__ part, int64_t km, int chunks,
+                                                          TO* __restrict__ g) {
+    int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    int l = threadIdx.x & 7;
+    TA acc = TA(0);
+    if (e < km)
+        for (int c = l; c < chunks; c += 8) acc += part[(int64_t)c * km + e];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (e < km && l == 0) g[e] = (TO)acc;
+}
+
+template <int NI>
+static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m, const double* O, int64_t ldo,
+                          int k, int64_t n, int fast, double* part, cudaStream_t st) {
+    dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
+    switch (p.nj) {
+        case 1: gram_dmma_kernel<NI, 1><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
+        case 2: gram_dmma_kernel<NI, 2><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
+        default: gram_dmma_kernel<NI, 4><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
+    }
+    return check_launch();
+}
+
+// simt plan: 8x8 tiles
+static GramPlan gram_plan_simt(int64_t m, int64_t k, int64_t n, int vec) {
+    GramPlan p;
+    p.ni = p.nj = 1;
+    p.tiles_i = (int)((k + 7) / 8);
+    p.tiles_j = (int)((m + 7) / 8);
+    int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
+    int64_t step = 32 * vec;
+    int64_t want = ((int64_t)sm_count() * 8 + tiles - 1) / tiles;
+    int64_t maxc = (n + GRAM_WARPS * step * 2 - 1) / (GRAM_WARPS * step * 2);
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    int64_t rows_per_cta = (n + want - 1) / want;
+    int64_t rpw = (rows_per_cta + GRAM_WARPS - 1) / GRAM_WARPS;
+    rpw = (rpw + step - 1) / step * step;
+    p.rows_per_warp = rpw;
+    p.chunks = (int)((n + rpw * GRAM_WARPS - 1) / (rpw * GRAM_WARPS));
+    return p;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" {
+
+// gram_mode: 0 = dtype default (fp64 -> DMMA, fp32 -> SIMT fp32 accumulate),
+//            1 = force SIMT, 2 = fp32 data with fp64 accumulation and fp64 output
+static int g_gram_force_simt = 0;
+void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on; }
+
+static size_t gram_ws_bytes_impl(int dtype, int64_t m, int64_t k, int64_t n, int acc64) {
+    if (m <= 0 || k <= 0 || n <= 0) return 0;
+    if (dtype == RL_F64 && !g_gram_force_simt) {
+        GramPlan p = gram_plan(m, k, n);
+        return (size_t)p.chunks * k * m * sizeof(double);
+    }
+    GramPlan p = gram_plan_simt(m, k, n, dtype == RL_F32 ? 4 : 2);
+    return (size_t)p.chunks * k * m * ((dtype == RL_F64 || acc64) ? 8 : 4);
+}
+
+size_t rl_gram_ws_bytes(int dtype, int64_t m, int64_t k, int64_t n) {
+    return gram_ws_bytes_impl(dtype, m, k, n, 0);
+}
+
+static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k,
+                     int64_t n, void* g, void* ws, size_t ws_bytes, int acc64, cudaStream_t st) {
+    if (m < 0 || k < 0 || n < 0 || m > INT32_MAX || k > INT32_MAX) return RL_E_ARG;
+    if (m == 0 || k == 0) return 0;
+    size_t esz = dtype == RL_F32 ? (acc64 ? 8 : 4) : 8;
+    if (dtype != RL_F32 && dtype != RL_F64) return RL_E_DTYPE;
+    if (n == 0) return (int)cudaMemsetAsync(g, 0, (size_t)k * m * esz, st);
+    if (ws_bytes < gram_ws_bytes_impl(dtype, m, k, n, acc64)) return RL_E_WORKSPACE;
+    int64_t km = k * m;
+    int rc;
+    int chunks;
+    if (dtype == RL_F64 && !g_gram_force_simt) {
+        GramPlan p = gram_plan(m, k, n);
+        int fast = host_aligned16(s) && host_aligned16(o) && (lds % 2 == 0) && (ldo % 2 == 0);
+        const double* S = (const double*)s;
+        const double* O = (const double*)o;
+        switch (p.ni) {
+            case 1: rc = launch_dmma_nj<1>(p, S, lds, (int)m, O, ldo, (int)k, n, fast, (double*)ws, st); break;
+            case 2: rc = launch_dmma_nj<2>(p, S, lds, (int)m, O, ldo, (int)k, n, fast, (double*)ws, st); break;
+            default: rc = launch_dmma_nj<4>(p, S, lds, (int)m, O, ldo, (int)k, n, fast, (double*)ws, st); break;
+        }
+        if (rc) return rc;
+        chunks = p.chunks;
+        gram_reduce_kernel<double, double><<<(unsigned)((km * 8 + 255) / 256), 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+        return check_launch();
+    }
+    GramPlan p = gram_plan_simt(m, k, n, dtype == RL_F32 ? 4 : 2);
+    dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
+    chunks = p.chunks;
+    unsigned rblocks = (unsigned)((km * 8 + 255) / 256);
+    if (dtype == RL_F64) {
+        int fast = host_aligned16(s) && host_aligned16(o) && (lds % 2 == 0) && (ldo % 2 == 0);
+        gram_simt_kernel<double, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const double*)s, lds, (int)m, (const double*)o, ldo, (int)k, n, p.rows_per_warp, fast, (double*)ws);
+        rc = check_launch(); if (rc) return rc;
+        gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+    } else if (acc64) {
+        int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
+        gram_simt_kernel<float, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_warp, fast, (double*)ws);
+        rc = check_launch(); if (rc) return rc;
+        gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+    } else {
+        int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
+        gram_simt_kernel<float, float, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_warp, fast, (float*)ws);
+        rc = check_launch(); if (rc) return rc;
+        gram_reduce_kernel<float, float><<<rblocks, 256, 0, st>>>((const float*)ws, km, chunks, (float*)g);
+    }
+    return check_launch();
+}
+
+int rl_gram(int dtype, const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k, int64_t n,
+            void* g, void* ws, size_t ws_bytes, void* stream) {
+    return gram_impl(dtype, s, lds, m, o, ldo, k, n, g, ws, ws_bytes, 0, as_stream(stream));
+}
+
+// fp32 (or fp64) data, fp64 accumulation, fp64 (k, m) result: the Gram used by
+// the on-device SVD / orthonormalisation, where squaring the condition number
+// in fp32 would lose the small singular values.
+size_t rl_gram_acc64_ws_bytes(int dtype, int64_t m, int64_t k, int64_t n) {
+    return gram_ws_bytes_impl(dtype, m, k, n, 1);
+}
+int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k,
+                  int64_t n, double* g, void* ws, size_t ws_bytes, void* stream) {
+    return gram_impl(dtype, s, lds, m, o, ldo, k, n, g, ws, ws_bytes, 1, as_stream(stream));
+}
+
+int rl_gram_h(int dtype, const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k, int64_t n,
+              void* g_h, void* stream) {
+    if (m < 0 || k < 0 || n < 0) return RL_E_ARG;
+    if (m == 0 || k == 0) return 0;
+    size_t w = dtype == RL_F32 ? 4 : dtype == RL_F64 ? 8 : 0;
+    if (!w) return RL_E_DTYPE;
+    size_t bytes = (size_t)k * m * w;
+    void *pinned = nullptr, *dev = nullptr, *ws = nullptr;
+    int rc = staging_acquire(bytes, &pinned, &dev);
+    if (rc) return rc;
+    size_t wsb = rl_gram_ws_bytes(dtype, m, k, n);
+    if (wsb) { rc = scratch_acquire(wsb, &ws); if (rc) return rc; }
+    rc = rl_gram(dtype, s, lds, m, o, ldo, k, n, dev, ws, wsb, stream);
+    if (rc) return rc;
+    RL_CUDA(cudaMemcpyAsync(pinned, dev, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    RL_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    memcpy(g_h, pinned, bytes);
+    return 0;
+}
+
+}  // extern "C"

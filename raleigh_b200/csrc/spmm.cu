@@ -1,0 +1,139 @@
+// CSR block SpMM  Y[v, r] = sum_{p in row r} val[p] * X[v, col[p]]
+// (SparseSymmetricMatrix.apply, sparse_mkl.py:42-48 -> mkl_?csrmm, mkl_wrap.py:274-276).
+// The device holds the full symmetric matrix (both triangles) as 0-based CSR.
+//
+// Algorithmic traffic: nnz*(w+4) + (nrows+1)*8 + 2*nrows*m*w bytes, 2*nnz*m flops.
+//
+// Mapping for VECTOR-MAJOR block vectors: lane = row, so for stencil / banded
+// matrices the 32 lanes of a warp gather 32 neighbouring components of one
+// vector -- a coalesced 128/256-byte request -- and the Y store is coalesced by
+// construction.  A warp stages the (col, val) entries of its 32 rows into shared
+// memory ONCE with coalesced loads and re-reads them from there for every group
+// of VG vectors, so the matrix is streamed from HBM exactly once per SpMM no
+// matter how many vectors the block has.  The X gathers go through L1/L2: the
+// reuse distance of a stencil (one grid plane) is L2-resident.
+#include "common.cuh"
+
+namespace rl {
+
+constexpr int SPMM_WARPS = 4;
+
+template <typename T, int VG>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+            const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
+            int m, int cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* sval = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap;
+    int32_t* scol = reinterpret_cast<int32_t*>(reinterpret_cast<T*>(smem_raw) + (size_t)SPMM_WARPS * cap) + (size_t)warp * cap;
+
+    const int64_t row0 = ((int64_t)blockIdx.x * SPMM_WARPS + warp) * 32;
+    if (row0 >= nrows) return;
+    const int64_t r = row0 + lane;
+    const bool live = r < nrows;
+    const int64_t p0 = live ? __ldg(indptr + r) : 0;
+    const int64_t p1 = live ? __ldg(indptr + r + 1) : 0;
+    const int64_t base = __shfl_sync(0xffffffffu, p0, 0);
+    const int64_t last_row = (row0 + 32 <= nrows ? row0 + 32 : nrows);
+    const int64_t end = __ldg(indptr + last_row);
+    const int64_t cnt = end - base;
+    const bool staged = cnt <= cap;
+    if (staged) {
+        for (int64_t e = lane; e < cnt; e += 32) {
+            scol[e] = __ldg(indices + base + e);
+            sval[e] = __ldg(values + base + e);
+        }
+        __syncwarp();
+    }
+    const int q0 = (int)(p0 - base), q1 = (int)(p1 - base);   // valid when staged
+
+    for (int v0 = 0; v0 < m; v0 += VG) {
+        T acc[VG];
+#pragma unroll
+        for (int g = 0; g < VG; ++g) acc[g] = T(0);
+        const T* xb = X + (int64_t)v0 * ldx;
+        const int nv = m - v0 < VG ? m - v0 : VG;
+        if (staged) {
+            if (nv == VG) {
+                int p = q0;
+                for (; p + 2 <= q1; p += 2) {
+                    const int c0 = scol[p], c1 = scol[p + 1];
+                    const T a0 = sval[p], a1 = sval[p + 1];
+                    T x0[VG], x1[VG];
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) { x0[g] = __ldg(xb + (int64_t)g * ldx + c0); x1[g] = __ldg(xb + (int64_t)g * ldx + c1); }
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) { acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]); }
+                }
+                if (p < q1) {
+                    const int c0 = scol[p];
+                    const T a0 = sval[p];
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                }
+            } else {
+                for (int p = q0; p < q1; ++p) {
+                    const int c0 = scol[p];
+                    const T a0 = sval[p];
+#pragma unroll
+                    for (int g = 0; g < VG; ++g)
+                        if (g < nv) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                }
+            }
+        } else {
+            for (int64_t p = p0; p < p1; ++p) {
+                const int c0 = __ldg(indices + p);
+                const T a0 = __ldg(values + p);
+#pragma unroll
+                for (int g = 0; g < VG; ++g)
+                    if (g < nv) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int g = 0; g < VG; ++g)
+                if (g < nv) Y[(int64_t)(v0 + g) * ldy + r] = acc[g];
+        }
+    }
+}
+
+template <typename T>
+static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
+                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, cudaStream_t st) {
+    // shared-memory capacity per warp: twice the average entries of 32 rows,
+    // rounded to a power of two in [256, 4096]
+    int64_t avg = nrows > 0 ? (nnz * 32 + nrows - 1) / nrows : 0;
+    int cap = 256;
+    while (cap < 2 * avg && cap < 4096) cap *= 2;
+    size_t smem = (size_t)SPMM_WARPS * cap * (sizeof(T) + 4);
+    constexpr int VG = 8;
+    auto kern = spmm_kernel<T, VG>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t blocks = (nrows + SPMM_WARPS * 32 - 1) / (SPMM_WARPS * 32);
+    kern<<<(unsigned)blocks, SPMM_WARPS * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
+                                                          (T*)y, ldy, (int)m, cap);
+    return check_launch();
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" {
+
+int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, void* stream) {
+    if (nrows < 0 || m < 0 || nnz < 0 || m > INT32_MAX) return RL_E_ARG;
+    if (nrows == 0 || m == 0) return 0;
+    if (x == y) return RL_E_ALIAS;
+    if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
+    if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
+    return RL_E_DTYPE;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// Block update  Out[j,:] = beta*Out[j,:] + alpha * sum_{i<k} Q[i,j] * X[i,:]
+// (Vectors.multiply: beta = 0, dense_cublas.py:271-299;  Vectors.add(other, s, q):
+// beta = 1, dense_cublas.py:317-342).  X is (k, n), Out is (m, n), vector-major;
+// Q is a small (k, m) coefficient matrix with arbitrary element strides.
+//
+// Algorithmic traffic: n*(k + m)*w bytes (beta = 0) or n*(k + 2m)*w (beta != 0);
+// 2*n*k*m flops.  HBM-bound up to m,k ~ 32 in fp64, FP64-pipe-bound beyond.
+//
+// Mapping: a thread owns VEC consecutive rows (one 128-bit load per X vector)
+// and TJ output vectors; the Q tile sits in shared memory and is read with
+// warp-broadcast 128-bit loads, so per X element loaded a thread issues TJ*VEC
+// FMAs and TJ*w/16 shared loads.  The CTA's j-groups share the same rows, so X
+// is fetched from HBM once and re-served by L1 to the other j-groups.
+#include "common.cuh"
+
+namespace rl {
+
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_TJ = 16;          // outputs per thread
+constexpr int UPD_JB = 64;          // outputs per CTA (4 j-groups)
+constexpr int UPD_KT = 32;          // Q rows staged per shared-memory tile
+
+template <typename T>
+__global__ void __launch_bounds__(UPD_THREADS, 2)
+update_kernel(T* __restrict__ Out, int64_t ldo, int m, const T* __restrict__ X, int64_t ldx, int k,
+              const T* __restrict__ Q, int64_t q_rs, int64_t q_cs, T alpha, T beta, int64_t n, int jgroups,
+              int fast) {
+    constexpr int V = Vec128<T>::N;
+    using VT = typename Vec128<T>::type;
+    __shared__ __align__(16) T Qs[UPD_KT][UPD_JB];
+
+    const int j_base = blockIdx.y * UPD_JB;
+    const int rthreads = UPD_THREADS / jgroups;            // threads along rows
+    const int jg = threadIdx.x / rthreads;                 // this thread's j-group
+    const int rt = threadIdx.x - jg * rthreads;
+    const int64_t r = ((int64_t)blockIdx.x * rthreads + rt) * V;
+    const int j0 = j_base + jg * UPD_TJ;
+    const bool row_ok = r < n;
+    const bool full = fast && (r + V <= n);
+
+    T acc[UPD_TJ][V];
+#pragma unroll
+    for (int j = 0; j < UPD_TJ; ++j)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[j][v] = T(0);
+
+    for (int i0 = 0; i0 < k; i0 += UPD_KT) {
+        const int kt = k - i0 < UPD_KT ? k - i0 : UPD_KT;
+        __syncthreads();
+        for (int e = threadIdx.x; e < UPD_KT * UPD_JB; e += UPD_THREADS) {
+            int ii = e / UPD_JB, jj = e % UPD_JB;
+            int j = j_base + jj;
+            Qs[ii][jj] = (ii < kt && j < m) ? __ldg(Q + (int64_t)(i0 + ii) * q_rs + (int64_t)j * q_cs) : T(0);
+        }
+        __syncthreads();
+        if (!row_ok) continue;
+        const T* px = X + (int64_t)i0 * ldx + r;
+        if (full) {
+            int ii = 0;
+            for (; ii + 4 <= kt; ii += 4) {
+                VT xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const VT*>(px + (int64_t)(ii + u) * ldx));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const T* xe = reinterpret_cast<const T*>(&xv[u]);
+#pragma unroll
+                    for (int j = 0; j < UPD_TJ; j += V) {
+                        VT qv = *reinterpret_cast<const VT*>(&Qs[ii + u][jg * UPD_TJ + j]);
+                        const T* qe = reinterpret_cast<const T*>(&qv);
+#pragma unroll
+                        for (int t = 0; t < V; ++t)
+#pragma unroll
+                            for (int v = 0; v < V; ++v) acc[j + t][v] = fma(qe[t], xe[v], acc[j + t][v]);
+                    }
+                }
+            }
+            for (; ii < kt; ++ii) {
+                VT xv = __ldg(reinterpret_cast<const VT*>(px + (int64_t)ii * ldx));
+                const T* xe = reinterpret_cast<const T*>(&xv);
+#pragma unroll
+                for (int j = 0; j < UPD_TJ; ++j) {
+                    T qv = Qs[ii][jg * UPD_TJ + j];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[j][v] = fma(qv, xe[v], acc[j][v]);
+                }
+            }
+        } else {
+            for (int ii = 0; ii < kt; ++ii) {
+                T xe[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) xe[v] = (r + v < n) ? __ldg(px + (int64_t)ii * ldx + v) : T(0);
+#pragma unroll
+                for (int j = 0; j < UPD_TJ; ++j) {
+                    T qv = Qs[ii][jg * UPD_TJ + j];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[j][v] = fma(qv, xe[v], acc[j][v]);
+                }
+            }
+        }
+    }
+    if (!row_ok) return;
+#pragma unroll
+    for (int j = 0; j < UPD_TJ; ++j) {
+        int jj = j0 + j;
+        if (jj >= m) break;
+        T* po = Out + (int64_t)jj * ldo + r;
+        if (full) {
+            VT res;
+            T* re = reinterpret_cast<T*>(&res);
+            if (beta != T(0)) {
+                VT old = *reinterpret_cast<const VT*>(po);
+                const T* oe = reinterpret_cast<const T*>(&old);
+#pragma unroll
+                for (int v = 0; v < V; ++v) re[v] = fma(alpha, acc[j][v], beta * oe[v]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) re[v] = alpha * acc[j][v];
+            }
+            *reinterpret_cast<VT*>(po) = res;
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (r + v < n) po[v] = beta != T(0) ? fma(alpha, acc[j][v], beta * po[v]) : alpha * acc[j][v];
+        }
+    }
+}
+
+template <typename T>
+static int update_impl(void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k, const void* q,
+                       int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, cudaStream_t st) {
+    constexpr int V = Vec128<T>::N;
+    int jb = (int)((m + UPD_JB - 1) / UPD_JB);
+    int jgroups = (int)((((m < UPD_JB) ? m : UPD_JB) + UPD_TJ - 1) / UPD_TJ);   // 1..4
+    if (jgroups == 3) jgroups = 4;                                              // keep 256 % jgroups == 0
+    int rthreads = UPD_THREADS / jgroups;
+    int64_t rows_per_cta = (int64_t)rthreads * V;
+    int64_t gx = (n + rows_per_cta - 1) / rows_per_cta;
+    int fast = host_aligned16(out) && host_aligned16(x) && (ldo % V == 0) && (ldx % V == 0);
+    dim3 grid((unsigned)gx, (unsigned)jb);
+    update_kernel<T><<<grid, UPD_THREADS, 0, st>>>((T*)out, ldo, (int)m, (const T*)x, ldx, (int)k, (const T*)q,
+                                                  q_rs, q_cs, (T)alpha, (T)beta, n, jgroups, fast);
+    return check_launch();
+}
+
+// beta-only pass (k == 0): Out = beta*Out
+template <typename T>
+__global__ void scale_all_kernel(T* out, int64_t ldo, int64_t m, int64_t n, T beta) {
+    for (int64_t j = blockIdx.y; j < m; j += gridDim.y)
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+            out[j * ldo + r] = beta == T(0) ? T(0) : beta * out[j * ldo + r];
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" {
+
+int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k, const void* q,
+              int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, void* stream) {
+    if (m < 0 || k < 0 || n < 0 || m > INT32_MAX || k > INT32_MAX) return RL_E_ARG;
+    if (m == 0 || n == 0) return 0;
+    if (dtype != RL_F32 && dtype != RL_F64) return RL_E_DTYPE;
+    cudaStream_t st = as_stream(stream);
+    if (k == 0 || alpha == 0.0) {
+        if (beta == 1.0) return 0;
+        int64_t gx = (n + 255) / 256; if (gx > 1024) gx = 1024;
+        dim3 g((unsigned)gx, (unsigned)(m < 65535 ? m : 65535));
+        if (dtype == RL_F32) scale_all_kernel<float><<<g, 256, 0, st>>>((float*)out, ldo, m, n, (float)beta);
+        else scale_all_kernel<double><<<g, 256, 0, st>>>((double*)out, ldo, m, n, beta);
+        return check_launch();
+    }
+    if (out == x) return RL_E_ALIAS;
+    if (dtype == RL_F32) return update_impl<float>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
+    return update_impl<double>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
+}
+
+int rl_update_h(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k,
+                const void* q_h, int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, void* stream) {
+    if (m < 0 || k < 0 || n < 0) return RL_E_ARG;
+    if (m == 0 || n == 0) return 0;
+    size_t w = dtype == RL_F32 ? 4 : dtype == RL_F64 ? 8 : 0;
+    if (!w) return RL_E_DTYPE;
+    if (k == 0) return rl_update(dtype, out, ldo, m, x, ldx, 0, nullptr, 0, 0, alpha, beta, n, stream);
+    if (q_rs < 0 || q_cs < 0) return RL_E_ARG;
+    // repack the (k, m) coefficients densely (row-major) into the staging ring
+    void *pinned = nullptr, *dev = nullptr;
+    int rc = staging_acquire((size_t)k * m * w, &pinned, &dev);
+    if (rc) return rc;
+    if (w == 8) {
+        const double* src = (const double*)q_h; double* dst = (double*)pinned;
+        for (int64_t i = 0; i < k; ++i)
+            for (int64_t j = 0; j < m; ++j) dst[i * m + j] = src[i * q_rs + j * q_cs];
+    } else {
+        const float* src = (const float*)q_h; float* dst = (float*)pinned;
+        for (int64_t i = 0; i < k; ++i)
+            for (int64_t j = 0; j < m; ++j) dst[i * m + j] = src[i * q_rs + j * q_cs];
+    }
+    RL_CUDA(cudaMemcpyAsync(dev, pinned, (size_t)k * m * w, cudaMemcpyHostToDevice, as_stream(stream)));
+    return rl_update(dtype, out, ldo, m, x, ldx, k, dev, m, 1, alpha, beta, n, stream);
+}
+
+}  // extern "C"

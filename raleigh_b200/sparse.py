@@ -1,0 +1,151 @@
+"""Sparse symmetric operator and preconditioner wrappers on the device.
+
+Drop-in for the parts of raleigh/algebra/sparse_mkl.py that lie on the
+preconditioned branch of partial_hevp (partial_hevp.py:202-224):
+`SparseSymmetricMatrix` (sparse_mkl.py:16-48) and `Operator`
+(sparse_mkl.py:143-154).  The reference has no GPU sparse path at all
+(README.md:49); MKL's `mkl_?csrmm` with descr 'SUNF' (mkl_wrap.py:264-276) is
+what `apply` computes.  `SparseSymmetricSolver` (PARDISO) and `IncompleteLU`
+are out of scope and raise.
+"""
+import numpy
+import scipy.sparse as scs
+
+from . import _lib
+from ._lib import lib, check
+from . import device as dev
+from .vectors import Vectors
+
+
+class SparseSymmetricMatrix:
+    """Y = A_sym X with A_sym the symmetric matrix whose upper triangle is
+    stored (the reference keeps only `triu(A)`; sparse_mkl.py:18-31).  The
+    device holds the FULL matrix as 0-based CSR (int64 indptr, int32 indices) so
+    that one gather-only SpMM kernel serves it; building it is one-off host
+    set-up, like the reference's own `triu` + `sort_indices`."""
+
+    def __init__(self, matrix):
+        try:
+            csr = matrix.csr()
+        except Exception:
+            csr = scs.triu(matrix, format='csr')
+            csr.sort_indices()
+        self.__csr = csr
+        dtype = csr.data.dtype.type
+        self.__code = _lib.dtype_code(dtype)          # raises ValueError for complex
+        strict = scs.triu(csr, k=1, format='csr')
+        full = (csr + strict.T).tocsr()
+        full.sort_indices()
+        self.__n = csr.shape[0]
+        self.__nnz = int(full.nnz)
+        indptr = numpy.ascontiguousarray(full.indptr, dtype=numpy.int64)
+        indices = numpy.ascontiguousarray(full.indices, dtype=numpy.int32)
+        values = numpy.ascontiguousarray(full.data, dtype=dtype)
+        self.__indptr = _to_device(indptr)
+        self.__indices = _to_device(indices)
+        self.__values = _to_device(values)
+        self.__diag = None
+        self.__full_diag = full.diagonal()
+
+    def size(self):
+        return self.__csr.shape[0]
+
+    def data_type(self):
+        return self.__csr.data.dtype
+
+    def csr(self):
+        return self.__csr
+
+    def nnz(self):
+        """Stored entries of the full (mirrored) device matrix."""
+        return self.__nnz
+
+    def diagonal(self):
+        return self.__full_diag
+
+    def apply(self, x, y):
+        if not isinstance(x, Vectors) or not isinstance(y, Vectors):
+            raise ValueError('SparseSymmetricMatrix.apply needs device Vectors')
+        m = x.nvec()
+        if m != y.nvec():
+            raise ValueError('Numbers of input and output vectors differ')
+        if x.dimension() != self.__n or y.dimension() != self.__n:
+            raise ValueError('Matrix and vectors dimensions incompatible')
+        if m < 1:
+            return
+        check(lib.rl_csr_spmm(self.__code, self.__n, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
+                              self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, dev.stream()))
+
+
+def _to_device(a):
+    buf = dev.Buffer(max(a.nbytes, 16))
+    if a.nbytes:
+        check(lib.rl_h2d(buf.ptr, dev.host_ptr(a), a.nbytes, dev.stream()))
+        check(lib.rl_sync_stream(dev.stream()))
+    return buf
+
+
+class DiagonalPreconditioner:
+    """Jacobi preconditioner y = x / diag(A) as a device operator: pass it as
+    `T` to partial_hevp (or wrap it in Operator).  The user-object contract of
+    the reference (`T.apply(x, y)` on 2-D ndarrays, partial_hevp.py:64-73) is
+    also honoured for host arrays so the same object works on the CPU oracle."""
+
+    def __init__(self, A):
+        if isinstance(A, SparseSymmetricMatrix):
+            d = A.diagonal()
+        elif scs.issparse(A):
+            d = A.diagonal()
+        else:
+            d = numpy.asarray(A).reshape(-1)
+        self.__inv = 1.0 / numpy.asarray(d)
+        self.__dev = {}
+
+    def _inv_on_device(self, dtype):
+        key = numpy.dtype(dtype).type
+        if key not in self.__dev:
+            self.__dev[key] = _to_device(numpy.ascontiguousarray(self.__inv, dtype=key))
+        return self.__dev[key]
+
+    def apply(self, x, y):
+        if isinstance(x, Vectors):
+            m = x.nvec()
+            if m < 1:
+                return
+            d = self._inv_on_device(x.data_type())
+            check(lib.rl_diag_mul(x._code, y._wptr(), y._ld, x._wptr(), x._ld, m, x.dimension(), d.ptr,
+                                  dev.stream()))
+        else:
+            y[...] = x * self.__inv[None, :].astype(x.dtype)
+
+
+class Operator:
+    """sparse_mkl.py:143-154.  The reference hands `x.data()`, `y.data()` (host
+    ndarrays that alias the vectors) to the user's `op.apply`; on the device
+    `data()` is a copy, so device-aware operators (anything that accepts
+    Vectors, e.g. DiagonalPreconditioner) get the Vectors themselves, and a
+    host-only user operator is served by a round trip through host memory."""
+
+    def __init__(self, op):
+        self.__op = op
+        self.__device_aware = isinstance(op, (DiagonalPreconditioner, SparseSymmetricMatrix)) or \
+            getattr(op, 'accepts_device_vectors', False)
+
+    def apply(self, x, y):
+        if self.__device_aware:
+            self.__op.apply(x, y)
+            return
+        xh = x.data()
+        yh = numpy.empty_like(xh)
+        self.__op.apply(xh, yh)
+        y.fill(yh)
+
+
+class SparseSymmetricSolver:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('shift-and-invert (PARDISO, sparse_mkl.py:51-119) is out of scope of raleigh_b200')
+
+
+class IncompleteLU:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('ILUT preconditioning (sparse_mkl.py:122-140) is out of scope of raleigh_b200')

@@ -1,0 +1,517 @@
+"""B200 implementation of RALEIGH's abstract `Vectors` type and dense `Matrix`.
+
+Drop-in for raleigh/algebra/dense_cublas.py (same class names, constructor
+signatures, methods, argument meaning and error behaviour -- the contract is
+the docstring at raleigh/core/solver.py:22-96 plus the extras the interfaces
+use), so the reference's unmodified core solver, partial_hevp and pca run on
+it.  Every method is one call into libraleigh_b200.so (hand-written sm_100a
+kernels); where the reference loops over vectors in Python and issues one
+cuBLAS call per vector, a single kernel handles the whole block.
+
+Layout: vector-major, vector j / component r at ``base + (j*ld + r)*itemsize``
+with ld padded to a 128-byte multiple; a selection window (first, nv) is a
+contiguous sub-block, so windows cost nothing.
+
+Semantics follow the NumPy backend (dense_numpy.py), which is the oracle every
+other backend is diffed against in the reference's own tests.
+"""
+import ctypes
+import numbers
+
+import numpy
+
+from . import _lib
+from ._lib import lib, check
+from . import device as dev
+
+
+def _np_type(t):
+    return numpy.dtype(t).type
+
+
+class Vectors:
+    """Block of vectors resident in HBM.  dense_cublas.py:17-632."""
+
+    MIN_INC = 16      # capacity growth policy of the reference (dense_cublas.py:424-425)
+    MAX_INC = 1024
+
+    # ------------------------------------------------------------------ ctor
+    def __init__(self, arg, nvec=0, data_type=None, shallow=False):
+        self._buf = None
+        self._off = 0                       # first vector of this object inside the buffer
+        if isinstance(arg, Vectors):
+            first, nv = arg.selected()
+            self._set_type(arg.data_type())
+            self._n = arg.dimension()
+            self._ld = arg._ld
+            if shallow:
+                # NumPy semantics (dense_ndarray.py:55-56): a view of the selected slice
+                self._buf = arg._buf
+                self._off = arg._off + first
+                self._cap = nv
+            else:
+                self._alloc(nv)
+                if nv > 0:
+                    check(lib.rl_copy(self._code, self._ptr(0), self._ld, arg._ptr(first), arg._ld,
+                                      nv, self._n, dev.stream()))
+            self._nvec = nv
+        elif isinstance(arg, Matrix):
+            if arg.order() != 'C_CONTIGUOUS':
+                raise ValueError('Vectors data must be C_CONTIGUOUS')
+            m, n = arg.shape()
+            self._set_type(arg.data_type())
+            self._n = n
+            self._ld = arg._ld
+            if shallow:
+                self._buf = arg._buf        # alias the matrix memory (dense_cublas.py:369-376)
+                self._off = arg._base
+                self._cap = m
+            else:
+                self._alloc(m)
+                if m > 0:
+                    check(lib.rl_copy(self._code, self._ptr(0), self._ld, arg._aptr(), arg._ld, m, n,
+                                      dev.stream()))
+            self._nvec = m
+        elif isinstance(arg, numpy.ndarray):
+            if arg.ndim != 2:
+                raise ValueError('Vectors data must be a 2D array')
+            m, n = arg.shape
+            self._set_type(arg.dtype.type)
+            self._n = n
+            self._ld = dev.padded_ld(n, self._w)
+            self._alloc(m)
+            self._nvec = m
+            if m > 0:
+                dev.upload_2d(self._ptr(0), self._ld * self._w, numpy.ascontiguousarray(arg))
+        elif isinstance(arg, numbers.Number):
+            self._set_type(numpy.float64 if data_type is None else data_type)
+            self._n = int(arg)
+            assert nvec >= 0
+            self._ld = dev.padded_ld(self._n, self._w)
+            self._alloc(int(nvec), zero=True)
+            self._nvec = int(nvec)
+        else:
+            raise ValueError('wrong argument %s in constructor' % repr(type(arg)))
+        self._sel = (0, self._nvec)
+        self._min_inc = Vectors.MIN_INC
+
+    def _set_type(self, t):
+        t = _np_type(t)
+        if t not in (numpy.float32, numpy.float64):
+            raise ValueError('data type %s not supported' % repr(t))
+        self._dtype = t
+        self._code = _lib.dtype_code(t)
+        self._w = 4 if t is numpy.float32 else 8
+
+    def _alloc(self, nvec, zero=False):
+        dev.require_cuda()
+        self._cap = nvec
+        self._off = 0
+        if nvec > 0:
+            self._buf = dev.Buffer(nvec * self._ld * self._w, zero=zero)
+        else:
+            self._buf = None
+
+    def _ptr(self, j):
+        """Device address of vector j (absolute index inside this object)."""
+        return self._buf.ptr + (self._off + j) * self._ld * self._w
+
+    def _wptr(self):
+        """Device address of the selected window (0 if nothing is allocated)."""
+        if self._buf is None:
+            return 0
+        return self._ptr(self._sel[0])
+
+    # ------------------------------------------- methods required by the solver
+    def new_vectors(self, arg=0, dim=None):
+        if isinstance(arg, numbers.Number):
+            return Vectors(self.dimension() if dim is None else dim, int(arg), self.data_type())
+        return Vectors(arg)
+
+    def clone(self):
+        return Vectors(self)
+
+    def dimension(self):
+        return self._n
+
+    def nvec(self):
+        return self._sel[1]
+
+    def select(self, nv, first=0):
+        assert nv <= self._nvec and first >= 0
+        self._sel = (first, nv)
+
+    def selected(self):
+        return self._sel
+
+    def data_type(self):
+        return self._dtype
+
+    def fill_random(self):
+        """Host NumPy RNG + H2D, exactly as the reference's GPU backend does
+        (dense_cublas.py:119-131), so that seeded runs reproduce across backends."""
+        m, n = self.nvec(), self._n
+        if m < 1:
+            return
+        data = numpy.random.rand(m, n).astype(self._dtype)
+        data *= 2
+        data -= 1
+        dev.upload_2d(self._wptr(), self._ld * self._w, data)
+
+    def fill_random_device(self, seed, vector0=0, row0=0):
+        """Counter-based device fill (no host traffic): element (j, r) depends only
+        on (seed, vector0 + j, row0 + r) -- partition independent."""
+        m = self.nvec()
+        if m < 1:
+            return
+        first = self._sel[0]
+        check(lib.rl_fill_uniform(self._code, self._wptr(), self._ld, m, self._n, int(seed),
+                                  int(vector0) + first, int(row0), dev.stream()))
+
+    def append(self, other, axis=0):
+        if other.nvec() < 1:
+            return
+        if axis == 1:
+            m, n = self.shape()
+            l, n_other = other.shape()
+            if m != l:
+                raise ValueError('Cannot append %d vectors to %d vectors' % (l, m))
+            if self.data_type() != other.data_type():
+                raise ValueError('Cannot append %s vectors to %s vectors'
+                                 % (repr(other.data_type()), repr(self.data_type())))
+            n_new = n + n_other
+            ld_new = dev.padded_ld(n_new, self._w)
+            buf = dev.Buffer(m * ld_new * self._w)
+            st = dev.stream()
+            check(lib.rl_copy(self._code, buf.ptr, ld_new, self._ptr(0), self._ld, m, n, st))
+            check(lib.rl_copy(self._code, buf.ptr + n * self._w, ld_new, other._ptr(0), other._ld, m, n_other, st))
+            self._buf, self._off, self._ld, self._n, self._cap = buf, 0, ld_new, n_new, m
+            return
+        i, m = self.selected()
+        j, l = other.selected()
+        if other.dimension() != self._n or other.data_type() != self._dtype:
+            raise ValueError('Cannot append incompatible vectors')
+        nvec = i + m + l
+        st = dev.stream()
+        if nvec > self._cap or self._buf is None:
+            cap = ((nvec - 1) // self._min_inc + 1) * self._min_inc
+            buf = dev.Buffer(cap * self._ld * self._w)
+            if i + m > 0:
+                check(lib.rl_copy(self._code, buf.ptr, self._ld, self._ptr(0), self._ld, i + m, self._n, st))
+            self._buf, self._off, self._cap = buf, 0, cap
+            if self._min_inc < Vectors.MAX_INC:
+                self._min_inc *= 2
+        check(lib.rl_copy(self._code, self._ptr(i + m), self._ld, other._ptr(j), other._ld, l, self._n, st))
+        self._nvec = nvec
+        self.select_all()
+
+    def copy(self, other, ind=None):
+        i, m = self.selected()
+        j, l = other.selected()
+        if ind is None:
+            assert m == l
+            if m < 1:
+                return
+            check(lib.rl_copy(self._code, other._ptr(j), other._ld, self._ptr(i), self._ld, m, self._n,
+                              dev.stream()))
+        else:
+            cnt = len(ind)
+            if cnt < 1:
+                return
+            idx = numpy.ascontiguousarray(ind, dtype=numpy.int64)
+            # absolute source indices, written at other's selection start (dense_numpy.py:42)
+            check(lib.rl_gather(self._code, other._ptr(j), other._ld, self._ptr(0), self._ld,
+                                idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), cnt, self._n, dev.stream()))
+
+    def _coeffs(self, s, count):
+        s = numpy.asarray(s)
+        if s.dtype.kind == 'c':
+            s = s.real
+        s = numpy.ascontiguousarray(s.reshape(-1)[:count], dtype=self._dtype)
+        if s.shape[0] < count:
+            raise ValueError('coefficient array too short')
+        return s
+
+    def scale(self, s, multiply=False):
+        f, m = self.selected()
+        if m < 1:
+            return
+        s = self._coeffs(s, m)
+        check(lib.rl_scale_h(self._code, self._wptr(), self._ld, m, self._n, dev.host_ptr(s),
+                             1 if multiply else 0, dev.stream()))
+
+    def dots(self, other, transp=False):
+        m, n = self.nvec(), self._n
+        if transp:
+            w = numpy.zeros((n,), dtype=self._dtype)
+            if n < 1 or m < 1:
+                return w
+            out = dev.Buffer(n * self._w)
+            check(lib.rl_dots_t(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, n, out.ptr,
+                                dev.stream()))
+            check(lib.rl_d2h(dev.host_ptr(w), out.ptr, n * self._w, dev.stream()))
+            return w
+        w = numpy.zeros((m,), dtype=self._dtype)
+        if m < 1:
+            return w
+        check(lib.rl_dots_h(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, n,
+                            dev.host_ptr(w), dev.stream()))
+        return w
+
+    def dot(self, other):
+        """G[i, j] = <other_i, self_j>, shape (other.nvec, self.nvec) (dense_numpy.py:78-82)."""
+        m, k = self.nvec(), other.nvec()
+        g = numpy.zeros((k, m), dtype=self._dtype)
+        if m < 1 or k < 1:
+            return g
+        if max(m, k) > Vectors._GEMM_THRESHOLD:
+            return self._dot_via_gemm(other)
+        check(lib.rl_gram_h(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, self._n,
+                            dev.host_ptr(g), dev.stream()))
+        return g
+
+    _GEMM_THRESHOLD = 2048   # blocks with more vectors than this are data matrices: use the GEMM
+
+    def _dot_via_gemm(self, other):
+        # q (k, m) = other (k, n) . self^T  == Matrix(self).apply(other)
+        m, k = self.nvec(), other.nvec()
+        q = Vectors(m, k, self._dtype)
+        check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, self._n, other._wptr(), other._ld,
+                                 q._wptr(), q._ld, k, 0, 1.0, 0.0, dev.stream()))
+        return q.data()
+
+    def _q_host(self, q, rows, cols):
+        q = numpy.asarray(q)
+        if q.ndim != 2 or q.shape[0] != rows or q.shape[1] != cols:
+            raise ValueError('coefficient matrix has shape %s, expected (%d, %d)' % (repr(q.shape), rows, cols))
+        if q.dtype.type is not self._dtype:
+            q = q.real.astype(self._dtype) if q.dtype.kind == 'c' else q.astype(self._dtype)
+        rs, cs = q.strides[0] // q.itemsize, q.strides[1] // q.itemsize
+        if q.strides[0] % q.itemsize or q.strides[1] % q.itemsize or rs < 0 or cs < 0:
+            q = numpy.ascontiguousarray(q)
+            rs, cs = q.strides[0] // q.itemsize, q.strides[1] // q.itemsize
+        return q, rs, cs
+
+    def multiply(self, q, output):
+        """output <- q^T . self  with q of shape (self.nvec, output.nvec) (dense_numpy.py:84-93)."""
+        k = self.nvec()
+        m = q.shape[1]
+        assert output.nvec() == m
+        if m < 1:
+            return
+        qh, rs, cs = self._q_host(q, k, m)
+        if k > Vectors._GEMM_THRESHOLD:
+            # self is a data matrix viewed as vectors (lra.py:236): out (m, n) = q^T (m, k) . S (k, n)
+            qt = Vectors(numpy.ascontiguousarray(qh.T))
+            check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, k, self._n, qt._wptr(), qt._ld,
+                                     output._wptr(), output._ld, m, 1, 1.0, 0.0, dev.stream()))
+            return
+        check(lib.rl_update_h(self._code, output._wptr(), output._ld, m, self._wptr(), self._ld, k,
+                              dev.host_ptr(qh), rs, cs, 1.0, 0.0, self._n, dev.stream()))
+
+    def add(self, other, s, q=None):
+        """Three modes (dense_numpy.py:95-105): scalar s (axpy), scalar s with q
+        (self += s q^T other), array s (per-vector axpy)."""
+        m = self.nvec()
+        if m < 1:
+            return
+        if numpy.isscalar(s):
+            if q is None:
+                check(lib.rl_axpy(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, self._n,
+                                  float(numpy.real(s)), dev.stream()))
+            else:
+                k = other.nvec()
+                if k < 1:
+                    return
+                qh, rs, cs = self._q_host(q, k, m)
+                check(lib.rl_update_h(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k,
+                                      dev.host_ptr(qh), rs, cs, float(numpy.real(s)), 1.0, self._n,
+                                      dev.stream()))
+        else:
+            sv = self._coeffs(s, m)
+            check(lib.rl_axpy_diag_h(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, self._n,
+                                     dev.host_ptr(sv), dev.stream()))
+
+    # ------------------------------------------------------------ other methods
+    def shape(self):
+        return (self._nvec, self._n)
+
+    def first(self):
+        return self._sel[0]
+
+    def select_all(self):
+        self.select(self._nvec)
+
+    def reference(self):
+        return Vectors(self, shallow=True)
+
+    def is_complex(self):
+        return False
+
+    def conjugate(self):
+        return
+
+    def data_size(self):
+        return self._w
+
+    def data_ptr(self):
+        return self._wptr()
+
+    def all_data_ptr(self):
+        return self._ptr(0) if self._buf is not None else 0
+
+    def leading_dimension(self):
+        return self._ld
+
+    def zero(self):
+        m = self.nvec()
+        if m < 1:
+            return
+        check(lib.rl_memset(self._wptr(), 0, m * self._ld * self._w, dev.stream()))
+
+    def fill(self, data):
+        if isinstance(data, numbers.Number):
+            data = numpy.full((self.nvec(), self._n), data, dtype=self._dtype)
+        m, n = data.shape
+        if m != self.nvec() or n != self._n:
+            raise ValueError('mismatching dimensions in fill()')
+        if m < 1:
+            return
+        if data.dtype.type is not self._dtype:
+            raise ValueError('mismatching data types in fill()')
+        dev.upload_2d(self._wptr(), self._ld * self._w, numpy.ascontiguousarray(data))
+
+    def data(self):
+        m = self.nvec()
+        if m < 1:
+            return numpy.ndarray((m, self._n), dtype=self._dtype)
+        return dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
+
+    def asarray(self):
+        return self.data().T
+
+    def orthogonalize(self, other):
+        """q = <other, self> (k, m); self -= q^T other; returns q as Vectors
+        (k vectors of dimension m).  dense_cublas.py:513-535."""
+        m, k, n = self.nvec(), other.nvec(), self._n
+        q = self.new_vectors(k, m)
+        if m < 1 or k < 1:
+            return q
+        st = dev.stream()
+        if max(m, k) > Vectors._GEMM_THRESHOLD:
+            # self is a data chunk: both products are real GEMMs
+            check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, n, other._wptr(), other._ld,
+                                     q._wptr(), q._ld, k, 0, 1.0, 0.0, st))
+        else:
+            wsb = lib.rl_gram_ws_bytes(self._code, m, k, n)
+            ws = dev.Buffer(wsb) if wsb else None
+            g = dev.Buffer(k * m * self._w)
+            check(lib.rl_gram(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, n, g.ptr,
+                              ws.ptr if ws else 0, wsb, st))
+            check(lib.rl_copy(self._code, q._wptr(), q._ld, g.ptr, m, k, m, st))
+        check(lib.rl_update(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, q._wptr(),
+                            q._ld, 1, -1.0, 1.0, n, st))
+        return q
+
+    def svd(self):
+        """Thin SVD of the selected block S (m, n): S = v diag(sigma) S_new with
+        orthonormal rows S_new overwriting self; returns (sigma, conj(v))
+        (dense_numpy.py:125-128; reference GPU: cusolverDn?gesvd, dense_cublas.py:537-591).
+        See svd.py for the on-device algorithm."""
+        from .svd import block_svd
+        return block_svd(self)
+
+
+class Matrix:
+    """Dense operator holder.  dense_cublas.py:635-776."""
+
+    def __init__(self, arg):
+        if isinstance(arg, Vectors):
+            f, m = arg.selected()
+            self._shape = (m, arg.dimension())
+            self._dtype = arg.data_type()
+            self._order = 'C_CONTIGUOUS'
+            ref = Vectors(arg, shallow=True)
+            self._buf, self._ld, self._base = ref._buf, ref._ld, ref._off
+        elif isinstance(arg, numpy.ndarray):
+            if arg.ndim != 2:
+                raise ValueError('Matrix data must be a 2D array')
+            self._shape = arg.shape
+            self._dtype = _np_type(arg.dtype.type)
+            if arg.flags['C_CONTIGUOUS']:
+                self._order = 'C_CONTIGUOUS'
+                stored = arg
+            elif arg.flags['F_CONTIGUOUS']:
+                self._order = 'F_CONTIGUOUS'
+                stored = arg.T          # device keeps the (N, M) C-ordered transpose
+            else:
+                raise ValueError('Matrix data must be either C- or F-contiguous')
+            if self._dtype not in (numpy.float32, numpy.float64):
+                raise ValueError('data type %s not supported' % repr(self._dtype))
+            rows, cols = stored.shape
+            w = stored.itemsize
+            self._ld = dev.padded_ld(cols, w)
+            self._base = 0
+            self._buf = dev.Buffer(max(rows, 1) * self._ld * w)
+            dev.upload_2d(self._buf.ptr, self._ld * w, stored)
+        else:
+            raise ValueError('wrong argument %s in Matrix constructor' % repr(type(arg)))
+        self._code = _lib.dtype_code(self._dtype)
+        self._w = 4 if self._dtype is numpy.float32 else 8
+
+    def _aptr(self):
+        return self._buf.ptr + self._base * self._ld * self._w
+
+    def data_ptr(self):
+        return self._aptr()
+
+    def order(self):
+        return self._order
+
+    def shape(self):
+        return self._shape
+
+    def data_type(self):
+        return self._dtype
+
+    def data_size(self):
+        return self._w
+
+    def is_complex(self):
+        return False
+
+    def fill(self, data):
+        stored = data if self._order == 'C_CONTIGUOUS' else data.T
+        dev.upload_2d(self._aptr(), self._ld * self._w, numpy.ascontiguousarray(stored, dtype=self._dtype))
+
+    def dots(self):
+        v = Vectors(self, shallow=True)
+        return v.dots(v)
+
+    def new_vectors(self, dim=None, nv=0):
+        if dim is None:
+            dim = self.shape()[1]
+        return Vectors(dim, nv, self.data_type())
+
+    def apply(self, x, y, transp=False):
+        """y = x . A^T, or y = x . A when transp (dense_cublas.py:732-776)."""
+        if x.data_type() != self._dtype or y.data_type() != self._dtype:
+            raise ValueError('Matrix and vectors data types differ')
+        m, n = self._shape
+        if transp:
+            if n != y.dimension() or m != x.dimension():
+                raise ValueError('Matrix and vectors dimensions incompatible')
+        else:
+            if m != y.dimension() or n != x.dimension():
+                raise ValueError('Matrix and vectors dimensions incompatible')
+        k = x.nvec()
+        if k != y.nvec():
+            raise ValueError('Numbers of input and output vectors differ')
+        if k < 1:
+            return
+        if self._order == 'C_CONTIGUOUS':
+            M, N, t = m, n, 1 if transp else 0
+        else:   # stored transposed: A = B^T with B (n, m) row-major
+            M, N, t = n, m, 0 if transp else 1
+        check(lib.rl_dense_apply(self._code, self._aptr(), self._ld, M, N, x._wptr(), x._ld, y._wptr(), y._ld,
+                                 k, t, 1.0, 0.0, dev.stream()))

@@ -1,0 +1,229 @@
+"""Pin the CPU oracle (oracle/) against golden vectors produced by the reference
+itself (tests/golden/make_golden.py) and the reference's known-answer tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+import oracle
+from oracle import algebra_np as K
+
+TAGS = ['d_300x12', 's_257x7', 'd_64x5']
+
+
+def _tol(dtype):
+    return 1e-12 if np.dtype(dtype) == np.float64 else 2e-5
+
+
+def _close(a, b, dtype):
+    scale = max(1.0, float(np.max(np.abs(b)))) if np.size(b) else 1.0
+    assert a.shape == b.shape
+    assert np.max(np.abs(a - b)) <= _tol(dtype) * scale * 10, np.max(np.abs(a - b))
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_functional_oracle_matches_reference(tag):
+    g = np.load(os.path.join(GOLDEN, 'algebra_%s.npz' % tag))
+    u, v, q, p, s, s0, A, ind = (g[k] for k in ('u', 'v', 'q', 'p', 's', 's0', 'A', 'ind'))
+    dt = u.dtype
+    nv = u.shape[0]
+    k = max(1, nv // 2)
+    _close(K.gram(u, v), g['dot'], dt)
+    _close(K.row_dots(u, v), g['dots'], dt)
+    _close(K.column_dots(u, v), g['dots_t'], dt)
+    f2, n2 = g['win_other']
+    _close(K.gram(u[1:1 + k], v[f2:f2 + n2]), g['dot_win'], dt)
+    w = K.combine(u, q)
+    _close(w, g['multiply'], dt)
+    _close(K.add_combined(v, w, -0.5, p), g['add_q'], dt)
+    _close(K.add_scaled(v, u, 2.0), g['add_s'], dt)
+    _close(K.add_per_vector(v, u, s), g['add_diag'], dt)
+    _close(K.scale_rows(v, s0), g['scale_div'], dt)
+    _close(K.scale_rows(v, s0, multiply=True), g['scale_mul'], dt)
+    exp = v.copy()
+    exp[nv - k:nv - k + len(ind)] = K.gather_rows(u, ind)
+    _close(exp, g['copy_ind'], dt)
+    sigma, vc, wt = K.thin_svd(u)
+    _close(sigma, g['svd_sigma'], dt)
+    recon = (vc.conj() * sigma[None, :]) @ wt
+    assert np.linalg.norm(recon - u) / np.linalg.norm(u) < 50 * _tol(dt)
+    xo, qo = K.project_out(v, g['onb'])
+    _close(qo, g['orth_q'], dt)
+    _close(xo, g['orth_x'], dt)
+    y = K.dense_apply(A, u)
+    _close(y, g['apply'], dt)
+    _close(K.dense_apply(A, y, transp=True), g['apply_t'], dt)
+    _close(K.row_sqnorms(A), g['mdots'], dt)
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_host_backend_matches_reference(tag):
+    """Same call sequence as make_golden.algebra_case, on oracle.Vectors."""
+    g = np.load(os.path.join(GOLDEN, 'algebra_%s.npz' % tag))
+    _run_backend_case(oracle.Vectors, oracle.Matrix, g, _close)
+
+
+def _run_backend_case(Vectors, Matrix, g, close):
+    u, v, q, p, s, s0, A, ind = (g[k] for k in ('u', 'v', 'q', 'p', 's', 's0', 'A', 'ind'))
+    dt = u.dtype
+    nv, n = u.shape
+    k = max(1, nv // 2)
+    U, V = Vectors(u.copy()), Vectors(v.copy())
+    close(U.dot(V), g['dot'], dt)
+    close(U.dots(V), g['dots'], dt)
+    close(U.dots(V, transp=True), g['dots_t'], dt)
+    U.select(k, 1)
+    V.select(int(g['win_other'][1]), int(g['win_other'][0]))
+    close(U.dot(V), g['dot_win'], dt)
+    U.select_all()
+    V.select_all()
+    W = Vectors(n, k, dt.type)
+    U.multiply(q, W)
+    close(W.data(), g['multiply'], dt)
+    V2 = Vectors(v.copy())
+    V2.add(W, -0.5, p)
+    close(V2.data(), g['add_q'], dt)
+    V2 = Vectors(v.copy())
+    V2.add(U, 2.0)
+    close(V2.data(), g['add_s'], dt)
+    V2 = Vectors(v.copy())
+    V2.add(U, s)
+    close(V2.data(), g['add_diag'], dt)
+    V2 = Vectors(v.copy())
+    V2.scale(s0)
+    close(V2.data(), g['scale_div'], dt)
+    V2 = Vectors(v.copy())
+    V2.scale(s0, multiply=True)
+    close(V2.data(), g['scale_mul'], dt)
+    V2 = Vectors(v.copy())
+    V2.select(k, nv - k)
+    U.copy(V2, ind)
+    V2.select_all()
+    close(V2.data(), g['copy_ind'], dt)
+    V2 = Vectors(v.copy())
+    U.select(k, 1)
+    V2.select(k, nv - k)
+    U.copy(V2)
+    V2.select_all()
+    U.select_all()
+    close(V2.data(), g['copy_win'], dt)
+    W2 = Vectors(u.copy())
+    sigma, qq = W2.svd()
+    close(np.asarray(sigma), g['svd_sigma'], dt)
+    recon = (qq.conj() * sigma[None, :]) @ W2.data()
+    assert np.linalg.norm(recon - u) / np.linalg.norm(u) < 200 * _tol(dt)
+    gram = W2.data() @ W2.data().T
+    assert np.max(np.abs(gram - np.eye(nv))) < 200 * _tol(dt)
+    X = Vectors(v.copy())
+    Qv = X.orthogonalize(Vectors(g['onb'].copy()))
+    close(Qv.data(), g['orth_q'], dt)
+    close(X.data(), g['orth_x'], dt)
+    X, Y = Vectors(u.copy()), Vectors(v.copy())
+    Y.select(k, 1)
+    X.append(Y)
+    close(X.data(), g['append0'], dt)
+    X = Vectors(u.copy())
+    X.append(Vectors(v.copy()), axis=1)
+    close(X.data(), g['append1'], dt)
+    X = Vectors(u.copy())
+    Z = X.reference()
+    Z.select(nv // 2, nv // 2)
+    Z.zero()
+    close(X.data(), g['ref_zero'], dt)
+    Aop = Matrix(A.copy())
+    x = Vectors(u.copy())
+    y = Vectors(A.shape[0], nv, dt.type)
+    Aop.apply(x, y)
+    close(y.data(), g['apply'], dt)
+    z = Vectors(n, nv, dt.type)
+    Aop.apply(y, z, transp=True)
+    close(z.data(), g['apply_t'], dt)
+    close(np.asarray(Aop.dots()), g['mdots'], dt)
+
+
+def test_sym_spmm_definition():
+    rng = np.random.default_rng(5)
+    import scipy.sparse as sp
+    A = sp.random(200, 200, density=0.05, random_state=3, format='csr')
+    A = (A + A.T).tocsr()
+    U = K.sym_upper_csr(A)
+    X = rng.standard_normal((6, 200))
+    assert np.allclose(K.sym_spmm(U, X), (A @ X.T).T, atol=1e-13)
+    # an unsymmetric input is symmetrised from its UPPER triangle, like MKL 'SUNF'
+    B = sp.random(50, 50, density=0.2, random_state=4, format='csr')
+    UB = K.sym_upper_csr(B)
+    full = sp.triu(B) + sp.triu(B, 1).T
+    X = rng.standard_normal((3, 50))
+    assert np.allclose(K.sym_spmm(UB, X), (full @ X.T).T, atol=1e-13)
+
+
+def test_laplacian_matches_reference_generator_and_analytic_spectrum(ref_root):
+    sys.path.insert(0, ref_root)
+    from raleigh.examples.laplace import lap3d
+    L = K.lap3d_csr(5, 4, 3, 1.0, 1.01, 1.02)
+    R = lap3d(5, 4, 3, 1.0, 1.01, 1.02)
+    assert abs(L - R).max() < 1e-9
+    ev = np.linalg.eigvalsh(K.lap3d_csr(4, 3, 3).toarray())
+    assert np.allclose(ev, K.lap3d_eigenvalues(4, 3, 3), rtol=1e-12)
+
+
+def _ref_solver(ref_root):
+    sys.path.insert(0, ref_root)
+    import scipy.linalg as sla
+    import raleigh.core.solver as rs
+
+    class Shim:
+        def __getattr__(self, name):
+            return getattr(sla, name)
+
+        def eigh(self, *a, turbo=None, **k):
+            return sla.eigh(*a, **k)
+    rs.sla = Shim()
+    return rs
+
+
+def run_solver(rs, Vectors, op, n, dtype, which, tol, block, T=None, crit='k eigenvector error', max_iter=1000):
+    np.random.seed(1)
+    opt = rs.Options()
+    opt.block_size = block
+    opt.max_iter = max_iter
+    opt.convergence_criteria = rs.DefaultConvergenceCriteria()
+    opt.convergence_criteria.set_error_tolerance(crit, tol)
+    v = Vectors(n, data_type=dtype)
+    solver = rs.Solver(rs.Problem(v, op))
+    if T is not None:
+        solver.set_preconditioner(T)
+    status = solver.solve(v, opt, which=which)
+    return status, solver.iteration, np.array(solver.eigenvalues), v
+
+
+def test_reference_solver_on_oracle_backend_reproduces_known_answers(ref_root):
+    """core_solver.py:65-71 doctest (58 iterations) and the golden sparse runs,
+    with the reference's solver driving oracle.Vectors / SparseSymmetricMatrix."""
+    rs = _ref_solver(ref_root)
+    g = np.load(os.path.join(GOLDEN, 'solver.npz'))
+    a = np.arange(1, 101).astype(np.float64)
+    st, it, lmd, _ = run_solver(rs, oracle.Vectors, oracle.Matrix(np.diag(a)), 100, np.float64, (6, 0), 1e-8, -1,
+                                crit='eigenvector error', max_iter=-1)
+    assert it == int(g['diag_iter']) == 58
+    assert np.allclose(lmd, [1, 2, 3, 4, 5, 6], atol=1e-10)
+    L = K.lap3d_csr(12, 12, 12)
+    st, it, lmd, _ = run_solver(rs, oracle.Vectors, oracle.SparseSymmetricMatrix(L), L.shape[0], np.float64,
+                                (6, 0), 1e-6, 8)
+    assert st == 0 and it == int(g['lap_iter'])
+    assert np.max(np.abs(lmd - g['lap_lmd']) / g['lap_lmd']) < 1e-10
+    assert np.max(np.abs(np.sort(lmd) - K.lap3d_eigenvalues(12, 12, 12)[:6])) < 1e-7
+
+
+def test_reference_solver_with_jacobi_on_oracle_backend(ref_root):
+    rs = _ref_solver(ref_root)
+    g = np.load(os.path.join(GOLDEN, 'solver.npz'))
+    from tests_common import spd_c3_like
+    A = spd_c3_like(3000)
+    st, it, lmd, _ = run_solver(rs, oracle.Vectors, oracle.SparseSymmetricMatrix(A), 3000, np.float64, (5, 0),
+                                1e-6, 8, T=oracle.Operator(oracle.Jacobi(A)))
+    assert st == 0 and it == int(g['spd_iter'])
+    assert np.max(np.abs(lmd - g['spd_lmd']) / g['spd_lmd']) < 1e-10
