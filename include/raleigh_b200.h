@@ -53,6 +53,16 @@ int rl_sync_stream(void* stream);
 /* counts kernels this library has launched since load (bench.py gpu_launches) */
 int64_t rl_launch_count(void);
 
+/* Optional per-entry-point device timing (CUDA events on the caller's stream
+ * around the device work of each call).  The reference only has wall-clock
+ * timers (partial_svd.py:261,290-291); bench.py reads these for the roofline.
+ * kinds 0..rl_profile_kinds()-1 are named by rl_profile_name(). */
+void rl_profile_enable(int on);
+void rl_profile_reset(void);
+int rl_profile_kinds(void);
+const char* rl_profile_name(int kind);
+int rl_profile_get(int kind, int64_t* count, double* ms, double* bytes, double* flops);
+
 /* ---- raw memory (cuda_wrap.py:142-153: malloc/free/memset/memcpy/memcpy2D;
  *      size_t sizes instead of the reference's c_int) ---------------------- */
 int rl_malloc(void** ptr, size_t bytes);

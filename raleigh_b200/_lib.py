@@ -30,6 +30,12 @@ PROTOTYPES = {
     'rl_sync_device': (c_int, []),
     'rl_sync_stream': (c_int, [c_vp]),
     'rl_launch_count': (c_i64, []),
+    'rl_profile_enable': (None, [c_int]),
+    'rl_profile_reset': (None, []),
+    'rl_profile_kinds': (c_int, []),
+    'rl_profile_name': (ctypes.c_char_p, [c_int]),
+    'rl_profile_get': (c_int, [c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl),
+                               ctypes.POINTER(c_dbl)]),
     'rl_malloc': (c_int, [ctypes.POINTER(c_vp), c_sz]),
     'rl_free': (c_int, [c_vp]),
     'rl_memset': (c_int, [c_vp, c_int, c_sz, c_vp]),
@@ -71,7 +77,7 @@ PROTOTYPES = {
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
-            'raleigh_b200: %s is missing -- build it with `python -m raleigh_b200.build` '
+            'raleigh_b200: %s is missing -- build it with `python raleigh_b200/build.py` '
             '(there is no CPU fallback)' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():

@@ -1,6 +1,6 @@
 """Build libraleigh_b200.so in-tree with nvcc for sm_100a.
 
-    python -m raleigh_b200.build [--force] [--verbose]
+    python raleigh_b200/build.py [--force] [--verbose]
 
 The library is a plain C-ABI shared object (include/raleigh_b200.h); it is
 compiled once per source change (content hash) and shipped to the GPU box with

@@ -72,6 +72,12 @@ def install(reference_path=None, sparse=True, dense=True):
         sys.path.insert(0, path)
     import raleigh
     import raleigh.algebra as algebra
+    # Import the reference's CPU selector FIRST so that arch='cpu' keeps its own
+    # algebra (dense_cpu.py:10-17 picks MKL cblas or NumPy) before dense_cblas is aliased.
+    try:
+        importlib.import_module('raleigh.algebra.dense_cpu')
+    except Exception:
+        pass
     for name, target in _ALIASES.items():
         if name == 'sparse_mkl' and not sparse:
             continue

@@ -3,11 +3,49 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace rl {
 
 int64_t g_launches = 0;
+int g_profile_on = 0;
+
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; double bytes, flops; };
+std::vector<ProfRec*> g_prof_open;           // spans recorded since the last collect
+struct ProfSum { int64_t count = 0; double ms = 0, bytes = 0, flops = 0; } g_prof_sum[PK_COUNT];
+const char* kProfNames[PK_COUNT] = {"gram", "update", "axpy", "axpy_diag", "scale", "dots", "dots_t", "copy",
+                                    "gather", "diag_mul", "spmm", "dense_apply", "dense_apply_tc", "syevj",
+                                    "fill_uniform"};
+void prof_collect() {
+    if (g_prof_open.empty()) return;
+    cudaDeviceSynchronize();
+    for (ProfRec* r : g_prof_open) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess) {
+            ProfSum& s = g_prof_sum[r->kind];
+            s.count += 1; s.ms += ms; s.bytes += r->bytes; s.flops += r->flops;
+        }
+        cudaEventDestroy(r->a); cudaEventDestroy(r->b);
+        delete r;
+    }
+    g_prof_open.clear();
+}
+}  // namespace
+
+void prof_begin(int kind, cudaStream_t st, double bytes, double flops, void** token) {
+    ProfRec* r = new ProfRec{kind, nullptr, nullptr, bytes, flops};
+    if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+    cudaEventRecord(r->a, st);
+    *token = r;
+}
+void prof_end(void* token, cudaStream_t st) {
+    ProfRec* r = (ProfRec*)token;
+    cudaEventRecord(r->b, st);
+    g_prof_open.push_back(r);
+    if (g_prof_open.size() >= 4096) prof_collect();   // bound the number of live events
+}
 
 int sm_count() {
     static int cached = 0;
@@ -126,6 +164,24 @@ int rl_device_info(int device, int* sm, int* cc_major, int* cc_minor, size_t* l2
         RL_CUDA(cudaMemGetInfo(&fr, &tot));
         *total_mem = tot;
     }
+    return 0;
+}
+
+void rl_profile_enable(int on) { g_profile_on = on; }
+void rl_profile_reset(void) {
+    prof_collect();
+    for (int i = 0; i < PK_COUNT; ++i) g_prof_sum[i] = ProfSum();
+}
+int rl_profile_kinds(void) { return PK_COUNT; }
+const char* rl_profile_name(int kind) { return (kind >= 0 && kind < PK_COUNT) ? kProfNames[kind] : ""; }
+int rl_profile_get(int kind, int64_t* count, double* ms, double* bytes, double* flops) {
+    if (kind < 0 || kind >= PK_COUNT) return RL_E_ARG;
+    prof_collect();
+    const ProfSum& s = g_prof_sum[kind];
+    if (count) *count = s.count;
+    if (ms) *ms = s.ms;
+    if (bytes) *bytes = s.bytes;
+    if (flops) *flops = s.flops;
     return 0;
 }
 

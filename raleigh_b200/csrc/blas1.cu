@@ -422,6 +422,7 @@ int rl_copy(int dtype, void* dst, int64_t ld_dst, const void* src, int64_t ld_sr
     if (!w) return RL_E_DTYPE;
     // the copy engine is not faster than SMs for D2D on B200, and a kernel keeps
     // stream ordering + launch accounting uniform
+    Span span(PK_COPY, as_stream(stream), 2.0 * m * n * w, 0.0);
     RL_DISPATCH(dtype, {
         CopyOp<T> op{(T*)dst, (const T*)src, ld_dst, ld_src};
         return launch_ew<T>(op, m, n, vec_ok<T>(dst, ld_dst, src, ld_src), as_stream(stream));
@@ -432,6 +433,7 @@ int rl_gather(int dtype, void* dst, int64_t ld_dst, const void* src_all, int64_t
               int64_t count, int64_t n, void* stream) {
     if (count < 0 || n < 0 || (count > 0 && !ind_h)) return RL_E_ARG;
     if (count == 0 || n == 0) return 0;
+    Span span(PK_GATHER, as_stream(stream), 2.0 * count * n * (dtype == RL_F32 ? 4 : 8), 0.0);
     RL_DISPATCH(dtype, {
         for (int64_t t0 = 0; t0 < count; t0 += GATHER_MAX) {
             int64_t c = count - t0 < GATHER_MAX ? count - t0 : GATHER_MAX;
@@ -449,6 +451,7 @@ int rl_fill_uniform(int dtype, void* x, int64_t ld, int64_t m, int64_t n, uint64
                     void* stream) {
     if (m < 0 || n < 0 || r0 < 0 || j0 < 0) return RL_E_ARG;
     if (m == 0 || n == 0) return 0;
+    Span span(PK_FILL, as_stream(stream), 1.0 * m * n * (dtype == RL_F32 ? 4 : 8), 0.0);
     RL_DISPATCH(dtype, {
         int64_t groups = n / (sizeof(T) == 4 ? 4 : 2) + 2;
         int64_t gx = (groups + 255) / 256;
@@ -462,6 +465,7 @@ int rl_fill_uniform(int dtype, void* x, int64_t ld, int64_t m, int64_t n, uint64
 int rl_axpy(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t m, int64_t n, double alpha,
             void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_AXPY, as_stream(stream), 3.0 * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
     RL_DISPATCH(dtype, {
         AxpyOp<T> op{(T*)y, (const T*)x, ldy, ldx, (T)alpha};
         return launch_ew<T>(op, m, n, vec_ok<T>(y, ldy, x, ldx), as_stream(stream));
@@ -471,6 +475,7 @@ int rl_axpy(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t
 int rl_axpy_diag(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t m, int64_t n, const void* s,
                  void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_AXPY_DIAG, as_stream(stream), 3.0 * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
     RL_DISPATCH(dtype, {
         AxpyDiagOp<T> op{(T*)y, (const T*)x, ldy, ldx, (const T*)s};
         return launch_ew<T>(op, m, n, vec_ok<T>(y, ldy, x, ldx), as_stream(stream));
@@ -479,6 +484,7 @@ int rl_axpy_diag(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx, in
 
 int rl_scale(int dtype, void* y, int64_t ldy, int64_t m, int64_t n, const void* s, int multiply, void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_SCALE, as_stream(stream), 2.0 * m * n * (dtype == RL_F32 ? 4 : 8), 1.0 * m * n);
     RL_DISPATCH(dtype, {
         ScaleOp<T> op{(T*)y, ldy, (const T*)s, multiply};
         return launch_ew<T>(op, m, n, vec_ok<T>(y, ldy), as_stream(stream));
@@ -488,6 +494,7 @@ int rl_scale(int dtype, void* y, int64_t ldy, int64_t m, int64_t n, const void* 
 int rl_diag_mul(int dtype, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t m, int64_t n, const void* d,
                 void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_DIAG_MUL, as_stream(stream), (2.0 * m + 1.0) * n * (dtype == RL_F32 ? 4 : 8), 1.0 * m * n);
     RL_DISPATCH(dtype, {
         DiagMulOp<T> op{(T*)y, (const T*)x, ldy, ldx, (const T*)d};
         return launch_ew<T>(op, m, n, vec_ok<T>(y, ldy, x, ldx) && host_aligned16(d), as_stream(stream));
@@ -504,12 +511,14 @@ size_t rl_dots_ws_bytes(int dtype, int64_t m, int64_t n) {
 int rl_dots(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo, int64_t m, int64_t n, void* w,
             void* ws, size_t ws_bytes, void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_DOTS, as_stream(stream), 2.0 * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
     RL_DISPATCH(dtype, { return dots_impl<T>(s, lds, o, ldo, m, n, w, ws, ws_bytes, as_stream(stream)); })
 }
 
 int rl_dots_t(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo, int64_t m, int64_t n, void* w,
               void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
+    Span span(PK_DOTS_T, as_stream(stream), 2.0 * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
     RL_DISPATCH(dtype, { return dots_t_impl<T>(s, lds, o, ldo, m, n, w, as_stream(stream)); })
 }
 

@@ -57,6 +57,26 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// ---- optional per-entry-point device timing (rl_profile_*) -------------------
+// A Span brackets the device work of one C-ABI call with two CUDA events on the
+// caller's stream when profiling is on (bench.py: roofline.achieved is measured
+// live from these); it costs one branch when profiling is off.
+enum ProfKind {
+    PK_GRAM = 0, PK_UPDATE, PK_AXPY, PK_AXPY_DIAG, PK_SCALE, PK_DOTS, PK_DOTS_T, PK_COPY, PK_GATHER,
+    PK_DIAG_MUL, PK_SPMM, PK_DENSE_APPLY, PK_DENSE_APPLY_TC, PK_SYEVJ, PK_FILL, PK_COUNT
+};
+extern int g_profile_on;
+void prof_begin(int kind, cudaStream_t st, double bytes, double flops, void** token);
+void prof_end(void* token, cudaStream_t st);
+struct Span {
+    void* token = nullptr;
+    cudaStream_t st;
+    Span(int kind, cudaStream_t s, double bytes, double flops) : st(s) {
+        if (g_profile_on) prof_begin(kind, s, bytes, flops, &token);
+    }
+    ~Span() { if (token) prof_end(token, st); }
+};
+
 // Library-owned scratch: a pinned host ring + a device ring used by the *_h
 // entry points to move small coefficient / result arrays (api.cu).
 struct Staging {

@@ -312,6 +312,9 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
     if (n == 0) return (int)cudaMemsetAsync(g, 0, (size_t)k * m * esz, st);
     if (ws_bytes < gram_ws_bytes_impl(dtype, m, k, n, acc64)) return RL_E_WORKSPACE;
     int64_t km = k * m;
+    const double wbytes = dtype == RL_F32 ? 4.0 : 8.0;
+    Span span(PK_GRAM, st, ((s == o ? 1.0 : 2.0) * 0 + 1.0 * (s == o ? m : m + k)) * n * wbytes + km * esz,
+              2.0 * n * m * k);
     int rc;
     int chunks;
     if (dtype == RL_F64 && !g_gram_force_simt) {

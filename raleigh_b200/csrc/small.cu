@@ -150,8 +150,12 @@ int rl_syevj(double* a, int64_t p, double* w, void* ws, size_t ws_bytes, int* sw
     int* order = (int*)(cs + P + 8);
     int* sweeps_d = order + 2 * P + 8;
     cudaStream_t st = as_stream(stream);
-    syevj_kernel<<<1, EIG_THREADS, 0, st>>>(a, (int)p, w, V, cs, order, sweeps_d);
-    int rc = check_launch();
+    int rc;
+    {
+        Span span(PK_SYEVJ, st, 2.0 * p * p * 8, 0.0);
+        syevj_kernel<<<1, EIG_THREADS, 0, st>>>(a, (int)p, w, V, cs, order, sweeps_d);
+        rc = check_launch();
+    }
     if (rc) return rc;
     if (sweeps_out_h) {
         RL_CUDA(cudaMemcpyAsync(sweeps_out_h, sweeps_d, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -131,6 +131,9 @@ int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, co
     if (nrows < 0 || m < 0 || nnz < 0 || m > INT32_MAX) return RL_E_ARG;
     if (nrows == 0 || m == 0) return 0;
     if (x == y) return RL_E_ALIAS;
+    const double w = dtype == RL_F32 ? 4.0 : 8.0;
+    Span span(PK_SPMM, as_stream(stream), nnz * (w + 4.0) + (nrows + 1) * 8.0 + 2.0 * nrows * m * w,
+              2.0 * nnz * m);
     if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
     if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
     return RL_E_DTYPE;

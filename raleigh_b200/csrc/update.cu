@@ -172,6 +172,8 @@ int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64
         return check_launch();
     }
     if (out == x) return RL_E_ALIAS;
+    Span span(PK_UPDATE, st, (1.0 * k + (beta != 0.0 ? 2.0 : 1.0) * m) * n * (dtype == RL_F32 ? 4 : 8),
+              2.0 * n * k * m);
     if (dtype == RL_F32) return update_impl<float>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
     return update_impl<double>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
 }

@@ -114,7 +114,7 @@ class Vectors:
 
     def _ptr(self, j):
         """Device address of vector j (absolute index inside this object)."""
-        return self._buf.ptr + (self._off + j) * self._ld * self._w
+        return self._buf.ptr + (self._off + int(j)) * self._ld * self._w
 
     def _wptr(self):
         """Device address of the selected window (0 if nothing is allocated)."""
@@ -139,7 +139,7 @@ class Vectors:
 
     def select(self, nv, first=0):
         assert nv <= self._nvec and first >= 0
-        self._sel = (first, nv)
+        self._sel = (int(first), int(nv))       # callers pass NumPy integers (lra.py:364)
 
     def selected(self):
         return self._sel

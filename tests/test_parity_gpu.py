@@ -1,0 +1,323 @@
+"""GPU parity: every Vectors / Matrix / sparse method of raleigh_b200 (through
+the C ABI) against the CPU oracle on the same seeded inputs, against the golden
+vectors produced by the reference, and -- at sizes the oracle cannot hold --
+through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+import oracle
+from oracle import algebra_np as K
+from test_oracle import _run_backend_case, TAGS
+
+pytestmark = pytest.mark.gpu
+
+# floating-point tolerances of BASELINE.json north_star: fp64 1e-10 on eigenvalues,
+# fp32 1e-5; per-kernel checks are tighter: a few ulps times the reduction length
+TOL = {np.float64: 1e-12, np.float32: 3e-5}
+
+
+def close(a, b, dtype, fac=10.0):
+    t = TOL[np.dtype(dtype).type]
+    scale = max(1.0, float(np.max(np.abs(b)))) if np.size(b) else 1.0
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if np.size(b) else 0.0
+    assert err <= t * scale * fac, err
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_golden_call_sequence(gpu_backend, tag):
+    g = np.load(os.path.join(GOLDEN, 'algebra_%s.npz' % tag))
+    _run_backend_case(gpu_backend.Vectors, gpu_backend.Matrix, g, close)
+
+
+SHAPES = [(1, 1, 1), (1, 7, 1), (3, 1, 2), (5, 33, 4), (16, 1000, 16), (17, 4099, 9), (32, 20000, 32),
+          (40, 5003, 33), (64, 3001, 70), (8, 262147, 8)]
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('m,n,k', SHAPES)
+def test_gram_update_dots_against_oracle(gpu_backend, dtype, m, n, k):
+    rng = np.random.RandomState(m * 1000 + k)
+    s = rng.randn(m, n).astype(dtype)
+    o = rng.randn(k, n).astype(dtype)
+    S, O = gpu_backend.Vectors(s), gpu_backend.Vectors(o)
+    fac = 10.0 * max(1.0, np.sqrt(n) / 10)
+    close(S.dot(O), K.gram(s, o), dtype, fac)
+    close(S.dot(S), K.gram(s, s), dtype, fac)
+    close(S.dots(S), K.row_dots(s, s), dtype, fac)
+    if m == k:
+        close(S.dots(O), K.row_dots(s, o), dtype, fac)
+        close(S.dots(O, transp=True), K.column_dots(s, o), dtype, fac)
+    q = rng.randn(m, k).astype(dtype)
+    out = gpu_backend.Vectors(n, k, dtype)
+    S.multiply(q, out)
+    close(out.data(), K.combine(s, q), dtype, fac)
+    # add with C-, F-ordered and strided q
+    p = rng.randn(k, m).astype(dtype)
+    for pv in (p, np.asfortranarray(p), rng.randn(2 * k, 2 * m).astype(dtype)[::2, ::2]):
+        S2 = gpu_backend.Vectors(s.copy())
+        S2.add(O, -0.75, pv)
+        close(S2.data(), K.add_combined(s, o, -0.75, np.asarray(pv)), dtype, fac)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_windows_and_zero_selection(gpu_backend, dtype):
+    rng = np.random.RandomState(7)
+    n, nv = 2050, 12
+    a = rng.randn(nv, n).astype(dtype)
+    b = rng.randn(nv, n).astype(dtype)
+    A, B = gpu_backend.Vectors(a.copy()), gpu_backend.Vectors(b.copy())
+    A.select(5, 3)
+    B.select(4, 7)
+    close(A.dot(B), K.gram(a[3:8], b[7:11]), dtype, 50)
+    A.select(0, 2)
+    assert A.dot(B).shape == (4, 0)
+    assert A.dots(A).shape == (0,)
+    A.scale(np.ones(0))
+    A.add(B, 1.0, np.zeros((4, 0), dtype=dtype))
+    A.zero()
+    A.select_all()
+    close(A.data(), a, dtype)
+    # clone of a window, reference of a window
+    A.select(4, 2)
+    C = A.clone()
+    assert C.nvec() == 4 and C.selected() == (0, 4)
+    close(C.data(), a[2:6], dtype)
+    R = A.reference()
+    R.zero()
+    A.select_all()
+    exp = a.copy()
+    exp[2:6] = 0
+    close(A.data(), exp, dtype)
+    # empty container + append growth (partial_hevp.py:211, solver lock events)
+    E = gpu_backend.Vectors(n, data_type=dtype)
+    assert E.nvec() == 0 and E.data().shape == (0, n)
+    for t in range(5):
+        B.select(3, t)
+        E.append(B)
+    B.select_all()
+    exp = np.concatenate([b[t:t + 3] for t in range(5)])
+    close(E.data(), exp, dtype)
+    assert E.nvec() == 15
+
+
+def test_error_behaviour(gpu_backend):
+    V, M = gpu_backend.Vectors, gpu_backend.Matrix
+    with pytest.raises(ValueError):
+        V('nope')
+    with pytest.raises(ValueError):
+        V(10, 2, np.int32)
+    a = M(np.zeros((4, 6), dtype=np.float32))
+    x, y = V(6, 2, np.float32), V(4, 2, np.float32)
+    a.apply(x, y)
+    with pytest.raises(ValueError):
+        a.apply(y, x)
+    with pytest.raises(ValueError):
+        a.apply(V(6, 2, np.float64), y)
+    with pytest.raises(ValueError):
+        a.apply(x, V(4, 3, np.float32))
+    with pytest.raises(ValueError):
+        M(np.zeros((8, 8))[::2, ::2])
+    with pytest.raises(ValueError):
+        V(M(np.asfortranarray(np.zeros((4, 6)))), shallow=True)
+    with pytest.raises(ValueError):
+        x.fill(np.zeros((3, 6), dtype=np.float32))
+    with pytest.raises(AssertionError):
+        x.select(3)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('M,N,k', [(5, 7, 3), (64, 64, 64), (130, 257, 17), (1000, 333, 128), (257, 1024, 128)])
+def test_dense_apply(gpu_backend, dtype, M, N, k):
+    rng = np.random.RandomState(M + N)
+    a = rng.randn(M, N).astype(dtype)
+    x = rng.randn(k, N).astype(dtype)
+    fac = 20 * max(1.0, np.sqrt(N) / 4)
+    for arr in (a, np.asfortranarray(a)):
+        A = gpu_backend.Matrix(arr)
+        assert A.order() == ('C_CONTIGUOUS' if arr.flags['C_CONTIGUOUS'] else 'F_CONTIGUOUS')
+        X = gpu_backend.Vectors(x.copy())
+        Y = gpu_backend.Vectors(M, k, dtype)
+        A.apply(X, Y)
+        y = K.dense_apply(a, x)
+        close(Y.data(), y, dtype, fac)
+        Z = gpu_backend.Vectors(N, k, dtype)
+        A.apply(Y, Z, transp=True)
+        close(Z.data(), K.dense_apply(a, y, transp=True), dtype, fac * np.sqrt(M))
+    A = gpu_backend.Matrix(a)
+    close(A.dots(), K.row_sqnorms(a), dtype, fac)
+    # Vectors(Matrix, shallow=True) aliases the matrix memory (dense_cublas.py:369-376)
+    V = gpu_backend.Vectors(A, shallow=True)
+    V.select(1, 0)
+    V.zero()
+    exp = a.copy()
+    exp[0] = 0
+    X = gpu_backend.Vectors(x.copy())
+    Y = gpu_backend.Vectors(M, k, dtype)
+    A.apply(X, Y)
+    close(Y.data(), K.dense_apply(exp, x), dtype, fac)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_data_matrix_as_vectors_paths(gpu_backend, dtype):
+    """lra.update shapes: thousands of short vectors aliasing a data chunk
+    (SURVEY section 3.4): dots, multiply(e1), add(vmean, -1, e1.T), orthogonalize."""
+    rng = np.random.RandomState(3)
+    n1, n, r = 3000, 200, 24
+    a = rng.randn(n1, n).astype(dtype)
+    A = gpu_backend.Matrix(a.copy())
+    v = gpu_backend.Vectors(A, shallow=True)
+    close(v.dots(v), K.row_dots(a, a), dtype, 50)
+    e1 = np.ones((n1, 1), dtype=dtype)
+    mean1 = v.new_vectors(1, n)
+    v.multiply(e1, mean1)
+    close(mean1.data(), K.combine(a, e1), dtype, 300)
+    mean = (a.sum(axis=0) / n1).reshape(1, n).astype(dtype)
+    vmean = v.new_vectors(mean)
+    v.add(vmean, -1.0, e1.T)
+    a = K.add_combined(a, mean, -1.0, e1.T)
+    close(v.data(), a, dtype, 50)
+    qmat, _ = np.linalg.qr(rng.randn(n, r).astype(dtype))
+    comps = np.ascontiguousarray(qmat.T)
+    left = v.orthogonalize(gpu_backend.Vectors(comps.copy()))
+    a_new, q = K.project_out(a, comps)
+    close(left.data(), q, dtype, 100)
+    close(v.data(), a_new, dtype, 100)
+    close(v.dots(v, transp=True), K.column_dots(a_new, a_new), dtype, 300)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_svd_identities(gpu_backend, dtype):
+    """tests_algebra.py:330-341 (reconstruction) + orthonormality + sigma vs LAPACK,
+    incl. an ill-conditioned block like the one _lra_ortho feeds (lra.py:473-482)."""
+    rng = np.random.RandomState(11)
+    for m, n, cond in [(1, 50, 1.0), (8, 300, 1.0), (16, 1000, 1e3), (40, 777, 1e2)]:
+        a = rng.randn(m, n).astype(dtype)
+        if cond > 1:
+            a *= np.logspace(0, -np.log10(cond), m).astype(dtype)[:, None]
+            a = (rng.randn(m, m).astype(dtype) @ a)
+        W = gpu_backend.Vectors(a.copy())
+        sigma, q = W.svd()
+        w = W.data()
+        t = TOL[dtype]
+        ref_sigma = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+        assert np.max(np.abs(sigma - ref_sigma)) <= 100 * t * ref_sigma[0]
+        assert np.all(np.diff(sigma) <= 1e-6 * sigma[0])
+        assert np.max(np.abs(w.astype(np.float64) @ w.T.astype(np.float64) - np.eye(m))) <= 200 * t
+        recon = (q.astype(np.float64) * sigma[None, :].astype(np.float64)) @ w.astype(np.float64)
+        assert np.linalg.norm(recon - a) / np.linalg.norm(a) <= 200 * t
+
+
+def test_lra_ortho_identity(gpu_backend):
+    """tests_algebra.py:43-82 (test_lra_ortho): v u^H is preserved, u orthonormalised."""
+    rng = np.random.RandomState(2)
+    k, nu, nv_ = 8, 500, 300
+    u0 = rng.randn(k, nu)
+    v0 = rng.randn(k, nv_)
+    Vc = gpu_backend.Vectors
+    u, v, wu, wv = Vc(u0.copy()), Vc(v0.copy()), Vc(nu, k), Vc(nv_, k)
+    u.copy(wu)
+    s, q = wu.svd()
+    v.multiply(q, wv)
+    wv.scale(s, multiply=True)
+    wv.copy(v)
+    s, q = v.svd()
+    wu.multiply(q, u)
+    v.scale(s, multiply=True)
+    prod0 = v0.T @ u0
+    prod1 = v.data().T @ u.data()
+    assert np.linalg.norm(prod1 - prod0) / np.linalg.norm(prod0) < 1e-12
+    g = u.data() @ u.data().T
+    assert np.max(np.abs(g - np.eye(k))) < 1e-12
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_spmm_and_jacobi(gpu_backend, dtype):
+    import scipy.sparse as sp
+    from tests_common import spd_c3_like
+    rng = np.random.RandomState(4)
+    cases = [K.lap3d_csr(7, 6, 5).astype(dtype), spd_c3_like(1111).astype(dtype)]
+    R = sp.random(300, 300, density=0.03, random_state=9, format='csr')
+    cases.append(((R + R.T) + sp.diags(np.arange(1.0, 301.0))).tocsr().astype(dtype))
+    # ragged: a few long rows (beyond the shared-memory staging capacity) + empty rows
+    D = sp.lil_matrix((700, 700))
+    D[0, :] = 1.0
+    D[:, 0] = 1.0
+    D[5, 5] = 2.0
+    cases.append(D.tocsr().astype(dtype))
+    for A in cases:
+        n = A.shape[0]
+        op = gpu_backend.SparseSymmetricMatrix(A)
+        assert op.size() == n and op.data_type() == np.dtype(dtype)
+        oop = oracle.SparseSymmetricMatrix(A)
+        for m in (1, 3, 8, 17):
+            x = rng.randn(m, n).astype(dtype)
+            X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(n, m, dtype)
+            op.apply(X, Y)
+            ref = K.sym_spmm(oop.csr(), x)
+            close(Y.data(), ref, dtype, 100 * max(1.0, float(abs(A).max())))
+    # upper-triangle semantics on an unsymmetric input (mkl 'SUNF')
+    B = sp.random(64, 64, density=0.2, random_state=1, format='csr').astype(dtype)
+    op = gpu_backend.SparseSymmetricMatrix(B)
+    x = rng.randn(4, 64).astype(dtype)
+    X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(64, 4, dtype)
+    op.apply(X, Y)
+    close(Y.data(), K.sym_spmm(K.sym_upper_csr(B), x), dtype, 50)
+    # Jacobi through Operator
+    A = spd_c3_like(1111).astype(dtype)
+    T = gpu_backend.Operator(gpu_backend.DiagonalPreconditioner(A))
+    x = rng.randn(5, 1111).astype(dtype)
+    X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(1111, 5, dtype)
+    T.apply(X, Y)
+    close(Y.data(), K.jacobi_apply(A.diagonal(), x), dtype, 10)
+    # host-only user preconditioner (reference contract, partial_hevp.py:64-73)
+    T2 = gpu_backend.Operator(oracle.Jacobi(A))
+    T2.apply(X, Y)
+    close(Y.data(), K.jacobi_apply(A.diagonal(), x), dtype, 10)
+
+
+def test_fill_random_host_stream_and_device_partition_independence(gpu_backend):
+    n = 1003
+    np.random.seed(1)
+    V = gpu_backend.Vectors(n, 4)
+    V.fill_random()
+    np.random.seed(1)
+    ref = K.uniform_fill_cublas(4, n)
+    assert np.array_equal(V.data(), ref)
+    # device fill: a shard (rows 200..700) reproduces the same rows of the full fill
+    full = gpu_backend.Vectors(n, 6)
+    full.fill_random_device(1234)
+    part = gpu_backend.Vectors(501, 6)
+    part.fill_random_device(1234, row0=200)
+    f = full.data()
+    assert np.array_equal(part.data(), f[:, 200:701])
+    assert abs(f.mean()) < 0.05 and abs(f.var() - 1 / 3) < 0.05 and f.min() >= -1 and f.max() < 1
+    f32 = gpu_backend.Vectors(n, 3, np.float32)
+    f32.fill_random_device(7)
+    p32 = gpu_backend.Vectors(n - 5, 3, np.float32)
+    p32.fill_random_device(7, row0=5)
+    assert np.array_equal(p32.data(), f32.data()[:, 5:])
+
+
+def test_large_properties(gpu_backend):
+    """Sizes the oracle cannot hold comfortably: linearity, symmetry, norms."""
+    n, m = 4_000_000, 32
+    X = gpu_backend.Vectors(n, m)
+    X.fill_random_device(5)
+    G = X.dot(X)
+    assert np.allclose(G, G.T, rtol=0, atol=1e-9 * n)
+    d = X.dots(X)
+    assert np.allclose(np.diag(G), d, rtol=1e-12)
+    assert np.allclose(d / n, 1 / 3, rtol=5e-3)
+    Y = gpu_backend.Vectors(n, m)
+    q = np.eye(m)[:, ::-1].copy()
+    X.multiply(q, Y)                      # permutation: exact
+    assert np.array_equal(Y.dots(Y), d[::-1])
+    Y.add(X, -1.0, q)                     # exact cancellation
+    assert np.max(np.abs(Y.dots(Y))) == 0.0
+    # determinism: same bits on repeat
+    assert np.array_equal(G, X.dot(X))
