@@ -11,7 +11,7 @@
 namespace rl {
 
 constexpr int EIG_THREADS = 1024;
-constexpr int EIG_MAX_SWEEPS = 40;
+constexpr int EIG_MAX_SWEEPS = 60;
 
 // workspace layout: V (p*p doubles) | cs (P doubles: c,s per pair) | top/bot (P ints) | flags
 __global__ void __launch_bounds__(EIG_THREADS)
@@ -46,7 +46,11 @@ syevj_kernel(double* __restrict__ A, int p, double* __restrict__ w, double* __re
         __syncthreads();
         if (tid == 0) { double t = 0; for (int i = 0; i < nt / 32; ++i) t += s_red[i]; s_diag = t; }
         __syncthreads();
-        if (s_off <= 1e-30 * (s_diag + s_off) || s_off == 0.0) break;
+        // backward-stable stop: ||off||_F <= p * eps * ||A||_F (rounding in the rotations
+        // re-creates off-diagonal noise of that size, so a tighter test never passes)
+        const double tol = fmax(1e-15, 2.2e-16 * p);
+        if (s_off <= tol * tol * (s_diag + s_off) || s_off == 0.0) break;
+        if (!(s_off == s_off) || !(s_diag == s_diag)) { sweep = -1; break; }   // NaN input
 
         for (int round = 0; round < P - 1; ++round) {
             // rotation angles for the disjoint pairs of this round
@@ -160,7 +164,7 @@ int rl_syevj(double* a, int64_t p, double* w, void* ws, size_t ws_bytes, int* sw
     if (sweeps_out_h) {
         RL_CUDA(cudaMemcpyAsync(sweeps_out_h, sweeps_d, sizeof(int), cudaMemcpyDeviceToHost, st));
         RL_CUDA(cudaStreamSynchronize(st));
-        if (*sweeps_out_h >= EIG_MAX_SWEEPS) return RL_E_NOTCONV;
+        if (*sweeps_out_h < 0) return RL_E_NOTCONV;      // NaN/Inf in the input
     }
     return 0;
 }

@@ -79,24 +79,28 @@ def block_svd(v):
     eps = float(numpy.finfo(dt).eps)
     tmp = v.new_vectors(m)
 
-    # pass 1
+    # pass 1.  Directions whose singular value is zero at the data precision
+    # (sigma <= sigma_max * m * eps) are NULL: they get weight 0 instead of 1/tiny,
+    # so rank-deficient blocks (lra.py:283-285 appends zero vectors) stay finite.
     w, V = device_eigh(_gram64(v), m)
     wmax = max(float(w[-1]), 0.0)
-    floor = wmax * (m * numpy.finfo(numpy.float64).eps) ** 2 + numpy.finfo(numpy.float64).tiny
-    lam = numpy.maximum(w, floor)
-    root = numpy.sqrt(lam)
-    _apply_left(v, V / root[None, :], tmp)           # S1 = diag(1/root) V^T S
+    live = w > wmax * (m * eps) ** 2
+    root = numpy.where(live, numpy.sqrt(numpy.where(live, w, 1.0)), 0.0)
+    iroot = numpy.where(live, 1.0 / numpy.where(live, root, 1.0), 0.0)
+    _apply_left(v, V * iroot[None, :], tmp)          # S1 = diag(1/root) V^T S
     B = V * root[None, :]                            # S = B S1
 
     # pass 2: re-orthonormalise when S1 S1^T differs from I beyond working precision
     g2 = _gram64(v)
     G2 = numpy.empty((m, m), dtype=numpy.float64)
     check(lib.rl_d2h(dev.host_ptr(G2), g2.ptr, m * m * 8, dev.stream()))
-    if numpy.amax(abs(G2 - numpy.eye(m))) > 4 * eps:
+    target = numpy.diag(live.astype(numpy.float64))
+    if numpy.amax(abs(G2 - target)) > 4 * eps:
         mu, W = device_eigh(g2, m)
-        mu = numpy.maximum(mu, numpy.finfo(numpy.float64).tiny)
-        rmu = numpy.sqrt(mu)
-        _apply_left(v, W / rmu[None, :], tmp)        # S2 = diag(1/rmu) W^T S1
+        live2 = mu > 1e-6
+        rmu = numpy.where(live2, numpy.sqrt(numpy.where(live2, mu, 1.0)), 0.0)
+        irmu = numpy.where(live2, 1.0 / numpy.where(live2, rmu, 1.0), 0.0)
+        _apply_left(v, W * irmu[None, :], tmp)       # S2 = diag(1/rmu) W^T S1
         B = (B @ W) * rmu[None, :]
 
     # small SVD of B through the device eigensolver: B^T B = Wb diag(s^2) Wb^T
