@@ -166,6 +166,21 @@ int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N,
                    const void* x, int64_t ldx, void* y, int64_t ldy, int64_t k,
                    int transp, double alpha, double beta, void* stream);
 
+/* Tensor-core path of the same product for fp32 (tcgen05.mma kind::tf32, TMEM
+ * accumulators, TMA-fed), fp32-accurate through the 3xTF32 split
+ * X.A ~= Xhi.Ahi + Xhi.Alo + Xlo.Ahi.  `a_lo` is the low part of the data
+ * matrix, produced once per matrix version by rl_split_tf32 (same shape and
+ * lda as `a`); the block's low part is built per call inside `ws`.
+ * Requirements: 16-byte aligned bases, lda and ldx multiples of 4
+ * (rl_dense_apply_tc_supported); any M, N, k. */
+int rl_dense_apply_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx);
+size_t rl_dense_apply_tc_ws_bytes(int64_t M, int64_t N, int64_t k, int transp);
+int rl_split_tf32(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                  int64_t cols, void* stream);
+int rl_dense_apply_tc(const void* a, const void* a_lo, int64_t lda, int64_t M, int64_t N,
+                      const void* x, int64_t ldx, void* y, int64_t ldy, int64_t k, int transp,
+                      double alpha, double beta, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- sparse symmetric operator ------------------------------------------- */
 /* SparseSymmetricMatrix.apply sparse_mkl.py:42-48 -> mkl_?csrmm mkl_wrap.py:274-276
  * (and mkl_?csrsymv :261-262 for m == 1).  The device holds the FULL symmetric

@@ -3,6 +3,13 @@
 #include "common.cuh"
 
 namespace rl {
+bool gemm_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx);
+int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_t N, const float* x, int64_t ldx,
+            float* y, int64_t ldy, int64_t k, int transp, double alpha, double beta, void* ws, size_t ws_bytes,
+            cudaStream_t st);
+size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t k, int transp);
+int split_tf32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+               cudaStream_t st);
 template <typename T>
 int gemm_simt(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
               int64_t k, int transp, double alpha, double beta, cudaStream_t st);
@@ -22,6 +29,34 @@ int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N, 
     if (dtype == RL_F32) return gemm_simt<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
     if (dtype == RL_F64) return gemm_simt<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
     return RL_E_DTYPE;
+}
+
+int rl_dense_apply_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx) {
+    return gemm_tc_supported(a, lda, x, ldx) ? 1 : 0;
+}
+
+size_t rl_dense_apply_tc_ws_bytes(int64_t M, int64_t N, int64_t k, int transp) {
+    if (M <= 0 || N <= 0 || k <= 0) return 0;
+    return gemm_tc_ws_bytes(M, N, k, transp);
+}
+
+int rl_split_tf32(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                  void* stream) {
+    if (rows < 0 || cols < 0 || (ld_src % 4) || (ld_dst % 4)) return RL_E_ARG;
+    return split_tf32((const float*)src, ld_src, (float*)dst, ld_dst, rows, cols, as_stream(stream));
+}
+
+int rl_dense_apply_tc(const void* a, const void* a_lo, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx,
+                      void* y, int64_t ldy, int64_t k, int transp, double alpha, double beta, void* ws,
+                      size_t ws_bytes, void* stream) {
+    if (M < 0 || N < 0 || k < 0) return RL_E_ARG;
+    if (k == 0 || (transp ? N : M) == 0) return 0;
+    if (!gemm_tc_supported(a, lda, x, ldx) || !host_aligned16(a_lo)) return RL_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    // algorithmic traffic: the hi and lo copies of the data matrix are both streamed
+    Span span(PK_DENSE_APPLY_TC, st, (2.0 * M * N + 1.0 * k * (M + N)) * 4.0, 2.0 * M * N * k);
+    return gemm_tc((const float*)a, (const float*)a_lo, lda, M, N, (const float*)x, ldx, (float*)y, ldy, k, transp,
+                   alpha, beta, ws, ws_bytes, st);
 }
 
 }  // extern "C"

@@ -44,7 +44,7 @@ class Buffer:
     (the reference's _Data, dense_cublas.py:801-811, minus the cudaFree that
     raises at interpreter exit)."""
 
-    __slots__ = ('tensor', 'ptr', 'nbytes')
+    __slots__ = ('tensor', 'ptr', 'nbytes', 'version')
 
     def __init__(self, nbytes, zero=False):
         require_cuda()
@@ -55,6 +55,7 @@ class Buffer:
             self.tensor = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
         self.ptr = self.tensor.data_ptr()
         self.nbytes = nbytes
+        self.version = 0      # bumped by every write through a Vectors/Matrix view
 
 
 def host_ptr(a):

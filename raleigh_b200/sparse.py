@@ -73,6 +73,7 @@ class SparseSymmetricMatrix:
             raise ValueError('Matrix and vectors dimensions incompatible')
         if m < 1:
             return
+        y._touch()
         check(lib.rl_csr_spmm(self.__code, self.__n, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
                               self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, dev.stream()))
 
@@ -113,6 +114,7 @@ class DiagonalPreconditioner:
             if m < 1:
                 return
             d = self._inv_on_device(x.data_type())
+            y._touch()
             check(lib.rl_diag_mul(x._code, y._wptr(), y._ld, x._wptr(), x._ld, m, x.dimension(), d.ptr,
                                   dev.stream()))
         else:

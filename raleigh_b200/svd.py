@@ -66,6 +66,7 @@ def _apply_left(v, coeff, tmp):
     """block <- coeff^T . block  (coeff is (m, m) host fp64) through `tmp`."""
     m, n = v.nvec(), v.dimension()
     q = numpy.ascontiguousarray(coeff, dtype=v.data_type())
+    v._touch()
     check(lib.rl_update_h(v._code, tmp._wptr(), tmp._ld, m, v._wptr(), v._ld, m, dev.host_ptr(q), m, 1,
                           1.0, 0.0, n, dev.stream()))
     check(lib.rl_copy(v._code, v._wptr(), v._ld, tmp._wptr(), tmp._ld, m, n, dev.stream()))

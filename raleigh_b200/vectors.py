@@ -116,6 +116,12 @@ class Vectors:
         """Device address of vector j (absolute index inside this object)."""
         return self._buf.ptr + (self._off + int(j)) * self._ld * self._w
 
+    def _touch(self):
+        """Record a write to the underlying buffer (a Matrix sharing it keeps a
+        derived low-part copy for the tensor-core path and must refresh it)."""
+        if self._buf is not None:
+            self._buf.version += 1
+
     def _wptr(self):
         """Device address of the selected window (0 if nothing is allocated)."""
         if self._buf is None:
@@ -157,6 +163,7 @@ class Vectors:
         data *= 2
         data -= 1
         dev.upload_2d(self._wptr(), self._ld * self._w, data)
+        self._touch()
 
     def fill_random_device(self, seed, vector0=0, row0=0):
         """Counter-based device fill (no host traffic): element (j, r) depends only
@@ -165,6 +172,7 @@ class Vectors:
         if m < 1:
             return
         first = self._sel[0]
+        self._touch()
         check(lib.rl_fill_uniform(self._code, self._wptr(), self._ld, m, self._n, int(seed),
                                   int(vector0) + first, int(row0), dev.stream()))
 
@@ -202,12 +210,14 @@ class Vectors:
             if self._min_inc < Vectors.MAX_INC:
                 self._min_inc *= 2
         check(lib.rl_copy(self._code, self._ptr(i + m), self._ld, other._ptr(j), other._ld, l, self._n, st))
+        self._touch()
         self._nvec = nvec
         self.select_all()
 
     def copy(self, other, ind=None):
         i, m = self.selected()
         j, l = other.selected()
+        other._touch()
         if ind is None:
             assert m == l
             if m < 1:
@@ -237,6 +247,7 @@ class Vectors:
         if m < 1:
             return
         s = self._coeffs(s, m)
+        self._touch()
         check(lib.rl_scale_h(self._code, self._wptr(), self._ld, m, self._n, dev.host_ptr(s),
                              1 if multiply else 0, dev.stream()))
 
@@ -300,6 +311,7 @@ class Vectors:
         if m < 1:
             return
         qh, rs, cs = self._q_host(q, k, m)
+        output._touch()
         if k > Vectors._GEMM_THRESHOLD:
             # self is a data matrix viewed as vectors (lra.py:236): out (m, n) = q^T (m, k) . S (k, n)
             qt = Vectors(numpy.ascontiguousarray(qh.T))
@@ -315,6 +327,7 @@ class Vectors:
         m = self.nvec()
         if m < 1:
             return
+        self._touch()
         if numpy.isscalar(s):
             if q is None:
                 check(lib.rl_axpy(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, self._n,
@@ -367,6 +380,7 @@ class Vectors:
         m = self.nvec()
         if m < 1:
             return
+        self._touch()
         check(lib.rl_memset(self._wptr(), 0, m * self._ld * self._w, dev.stream()))
 
     def fill(self, data):
@@ -379,6 +393,7 @@ class Vectors:
             return
         if data.dtype.type is not self._dtype:
             raise ValueError('mismatching data types in fill()')
+        self._touch()
         dev.upload_2d(self._wptr(), self._ld * self._w, numpy.ascontiguousarray(data))
 
     def data(self):
@@ -398,6 +413,7 @@ class Vectors:
         if m < 1 or k < 1:
             return q
         st = dev.stream()
+        self._touch()
         if max(m, k) > Vectors._GEMM_THRESHOLD:
             # self is a data chunk: both products are real GEMMs
             check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, n, other._wptr(), other._ld,
@@ -458,6 +474,26 @@ class Matrix:
             raise ValueError('wrong argument %s in Matrix constructor' % repr(type(arg)))
         self._code = _lib.dtype_code(self._dtype)
         self._w = 4 if self._dtype is numpy.float32 else 8
+        self._lo = None               # low part of the 3xTF32 split (tensor-core path)
+        self._lo_version = -1
+
+    TC_MIN_VECTORS = 8                # below this the FMA-pipe kernel is used
+
+    def _stored_shape(self):
+        m, n = self._shape
+        return (m, n) if self._order == 'C_CONTIGUOUS' else (n, m)
+
+    def _lo_ptr(self):
+        """Device copy of a - tf32(a), refreshed whenever the matrix memory has
+        been written since it was built (vectors aliasing the matrix bump the
+        buffer version, e.g. lra.update centring a chunk in place)."""
+        rows, cols = self._stored_shape()
+        if self._lo is None:
+            self._lo = dev.Buffer(max(rows, 1) * self._ld * 4)
+        if self._lo_version != self._buf.version:
+            check(lib.rl_split_tf32(self._aptr(), self._ld, self._lo.ptr, self._ld, rows, cols, dev.stream()))
+            self._lo_version = self._buf.version
+        return self._lo.ptr
 
     def _aptr(self):
         return self._buf.ptr + self._base * self._ld * self._w
@@ -482,6 +518,7 @@ class Matrix:
 
     def fill(self, data):
         stored = data if self._order == 'C_CONTIGUOUS' else data.T
+        self._buf.version += 1
         dev.upload_2d(self._aptr(), self._ld * self._w, numpy.ascontiguousarray(stored, dtype=self._dtype))
 
     def dots(self):
@@ -513,5 +550,13 @@ class Matrix:
             M, N, t = m, n, 1 if transp else 0
         else:   # stored transposed: A = B^T with B (n, m) row-major
             M, N, t = n, m, 0 if transp else 1
+        y._touch()
+        if (self._dtype is numpy.float32 and k >= Matrix.TC_MIN_VECTORS and
+                lib.rl_dense_apply_tc_supported(self._aptr(), self._ld, x._wptr(), x._ld)):
+            wsb = lib.rl_dense_apply_tc_ws_bytes(M, N, k, t)
+            ws = dev.Buffer(wsb)
+            check(lib.rl_dense_apply_tc(self._aptr(), self._lo_ptr(), self._ld, M, N, x._wptr(), x._ld,
+                                        y._wptr(), y._ld, k, t, 1.0, 0.0, ws.ptr, wsb, dev.stream()))
+            return
         check(lib.rl_dense_apply(self._code, self._aptr(), self._ld, M, N, x._wptr(), x._ld, y._wptr(), y._ld,
                                  k, t, 1.0, 0.0, dev.stream()))

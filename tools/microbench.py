@@ -142,23 +142,37 @@ def spmm_suite(out, name, A, m, dtype):
          2.0 * nnz * m)
 
 
-def gemm_suite(out, M, N, k, reps=3):
-    a = torch.randn(M, N, dtype=torch.float32, device='cuda')
-    lda = N
+def gemm_suite(out, M, N, k, reps=5):
+    a = (torch.randn(M, N, dtype=torch.float32, device='cuda')).cpu().numpy()
+    A = rb.Matrix(a)
     x = rb.Vectors(N, k, np.float32)
     y = rb.Vectors(M, k, np.float32)
     x.fill_random_device(4)
     fl = 2.0 * M * N * k
     by = M * N * 4 + k * (M + N) * 4
-    f = lambda: check(lib.rl_dense_apply(0, a.data_ptr(), lda, M, N, x._wptr(), x._ld, y._wptr(), y._ld, k, 0, 1.0, 0.0, dev.stream()))
-    ms, best = timeit(f, reps=reps, warm=1)
-    emit(out, 'dense_apply', 'A=%dx%d,k=%d,f32' % (M, N, k), ms, best, by, fl)
-    f = lambda: check(lib.rl_dense_apply(0, a.data_ptr(), lda, M, N, y._wptr(), y._ld, x._wptr(), x._ld, k, 1, 1.0, 0.0, dev.stream()))
-    ms, best = timeit(f, reps=reps, warm=1)
-    emit(out, 'dense_apply_T', 'A=%dx%d,k=%d,f32' % (M, N, k), ms, best, by, fl)
+    shape = 'A=%dx%d,k=%d,f32' % (M, N, k)
+    A.apply(x, y)                       # builds the low part once
+    ms, best = timeit(lambda: A.apply(x, y), reps=reps, warm=1)
+    emit(out, 'dense_apply_tc', shape, ms, best, 2 * by, fl, 'bytes count hi+lo copies of A')
+    ms, best = timeit(lambda: A.apply(y, x, transp=True), reps=reps, warm=1)
+    emit(out, 'dense_apply_tc_T', shape, ms, best, 2 * by, fl, 'bytes count hi+lo copies of A')
+    f = lambda: check(lib.rl_dense_apply(0, A._aptr(), A._ld, M, N, x._wptr(), x._ld, y._wptr(), y._ld, k, 0, 1.0, 0.0, dev.stream()))
+    ms, best = timeit(f, reps=2, warm=1)
+    emit(out, 'dense_apply_simt', shape, ms, best, by, fl)
+    at = torch.as_tensor(a, device='cuda')
     xt = torch.randn(k, N, dtype=torch.float32, device='cuda')
-    ms, best = timeit(lambda: torch.matmul(xt, a.T), reps=reps, warm=1)
-    emit(out, 'torch_matmul_fp32(ref)', 'A=%dx%d,k=%d,f32' % (M, N, k), ms, best, by, fl, 'cuBLAS SGEMM incumbent')
+    ms, best = timeit(lambda: torch.matmul(xt, at.T), reps=reps, warm=1)
+    emit(out, 'torch_matmul_fp32(ref)', shape, ms, best, by, fl, 'cuBLAS SGEMM incumbent')
+    # accuracy of the 3xTF32 split against an fp64 product
+    A.apply(x, y)
+    ref = (torch.as_tensor(x.data(), device='cuda').double() @ at.double().T)
+    err = ((torch.as_tensor(y.data(), device='cuda').double() - ref).abs().max() / ref.abs().max()).item()
+    cub = ((torch.matmul(torch.as_tensor(x.data(), device='cuda'), at.T).double() - ref).abs().max() / ref.abs().max()).item()
+    print(json.dumps({'kernel': 'dense_apply_tc', 'shape': shape, 'max_rel_err_vs_fp64': err, 'cublas_sgemm_err': cub}), flush=True)
+    for kk in (1, 8):
+        xs = rb.Vectors(N, kk, np.float32); ys = rb.Vectors(M, kk, np.float32); xs.fill_random_device(5)
+        ms, best = timeit(lambda: A.apply(xs, ys), reps=3, warm=1)
+        emit(out, 'dense_apply(k=%d)' % kk, shape, ms, best, M * N * 4.0, 2.0 * M * N * kk)
 
 
 def eig_suite(out):
@@ -205,6 +219,6 @@ if __name__ == '__main__':
                                  2661, 2662, 2214, 2215, 2216, 2217, 3100, 3101, 3102])))
         spmm_suite(out, 'c3like_55nnz', spd_c3_like(140874, offsets=offs), 32, np.float64)
     if 'gemm' in only:
-        gemm_suite(out, 12000, 39375 if not args.quick else 8192, 128)
+        gemm_suite(out, 12000, 39375, 128)
     if 'eig' in only:
         eig_suite(out)
