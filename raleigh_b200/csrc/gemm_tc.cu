@@ -23,10 +23,11 @@
 // in a fixed order -> deterministic.
 //
 // UMMA shared-memory descriptors follow the canonical SWIZZLE_128B layouts
-// (K-major: 8-row x 128-byte atoms, SBO = 1024 B;  MN-major: 32-element x 8-K
-// atoms, LBO = bytes between 32-wide MN blocks, SBO = 1024 B), which is exactly
-// what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B and a 128-byte inner extent
-// writes.  Out-of-bounds parts of a box are zero-filled by TMA, so ragged
+// (K-major: SWIZZLE_128B, 8-row x 128-byte atoms, SBO = 1024 B;  MN-major tf32:
+// SWIZZLE_128B_BASE32B, 32-element x 4-K atoms, LBO = bytes between 32-wide MN
+// blocks, SBO = 512 B), which is exactly what a TMA box with
+// CU_TENSOR_MAP_SWIZZLE_128B (resp. ..._128B_ATOM_32B) and a 128-byte inner
+// extent writes.  Out-of-bounds parts of a box are zero-filled by TMA, so ragged
 // M, N, K and fewer than 128 vectors need no special code in the main loop.
 #include <cuda.h>
 #include "common.cuh"
@@ -105,12 +106,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte chunks XOR row%8; K-major operands),
+//         1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4) -- the only layout the
+//             tensor core accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = 2) {
     uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(lbo_bytes >> 4) << 16;
     d |= (uint64_t)(sbo_bytes >> 4) << 32;
     d |= 1ull << 46;      // descriptor version (Blackwell)
-    d |= 2ull << 61;      // layout type SWIZZLE_128B
+    d |= (uint64_t)layout << 61;
     return d;
 }
 
@@ -203,8 +208,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                             ah = umma_desc(sa_hi + s * 32, 16, 1024);
                             al = umma_desc(sa_lo + s * 32, 16, 1024);
                         } else {
-                            ah = umma_desc(sa_hi + s * 1024, 4096, 1024);
-                            al = umma_desc(sa_lo + s * 1024, 4096, 1024);
+                            // MN-major: 32-float x 4-K atoms (512 B); MN blocks 4096 B apart
+                            ah = umma_desc(sa_hi + s * 1024, 4096, 512, 1);
+                            al = umma_desc(sa_lo + s * 1024, 4096, 512, 1);
                         }
                         // small terms first, then the leading product
                         tc_mma_tf32(d_tmem, xl, ah, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
@@ -333,7 +339,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_inner,
-                    int box_rows) {
+                    int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return RL_E_ARG;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
@@ -341,7 +347,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t 
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : RL_E_ARG;
 }
@@ -398,8 +404,8 @@ int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_
         if (!rc) rc = make_map(&mah, a_hi, N, M, lda, TC_BK, TC_BN);
         if (!rc) rc = make_map(&mal, a_lo, N, M, lda, TC_BK, TC_BN);
     } else {
-        if (!rc) rc = make_map(&mah, a_hi, N, M, lda, 32, TC_BK);
-        if (!rc) rc = make_map(&mal, a_lo, N, M, lda, 32, TC_BK);
+        if (!rc) rc = make_map(&mah, a_hi, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!rc) rc = make_map(&mal, a_lo, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     }
     if (rc) return rc;
     TcParams p;
