@@ -192,6 +192,15 @@ int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr,
                 const int32_t* indices, const void* values, const void* x, int64_t ldx,
                 void* y, int64_t ldy, int64_t m, void* stream);
 
+/* Same product from the SELL-32 layout (sliced ELLPACK, 32-row slices): entry j
+ * of row 32*s + l is stored at slice_ptr[s] + 32*j + l; padding entries have
+ * val = 0 and any valid column.  `nnz` is the number of true entries (profiling
+ * only).  Coalesced matrix reads without staging; preferred when the padding
+ * overhead is small (SparseSymmetricMatrix decides at construction). */
+int rl_sell_spmm(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const int64_t* slice_ptr,
+                 const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y,
+                 int64_t ldy, int64_t m, void* stream);
+
 /* ---- small dense algebra on device (no host LAPACK) ----------------------- */
 /* Symmetric eigen-decomposition of the (p, p) row-major matrix `a` (fp64) by
  * cyclic Jacobi rotations: on return w[0..p) ascending eigenvalues and a holds

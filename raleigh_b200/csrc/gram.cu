@@ -27,30 +27,38 @@ constexpr int GRAM_WARPS = 4;
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;
 
 struct GramPlan {
-    int ni, nj;          // 8-wide fragments per warp tile along k (other) and m (self)
+    int ni, nj, js;      // 8-wide fragments per WARP tile along k (other) and m (self); warps side by side along m
     int tiles_i, tiles_j;
     int chunks;          // row chunks (CTAs along the reduction)
-    int64_t rows_per_warp;
+    int64_t rows_per_cta;
 };
+
+// A CTA (4 warps) owns an (8*NI) x (8*NJ*JS) tile of G; its 4/JS row-warps
+// interleave 16-row steps so the CTA reads 4/JS*128 contiguous bytes of every
+// vector per step.  Measured on B200 (profiles/r1c_kernel_tuning.md): the kernel is
+// bound by the number of load requests, not by occupancy -- one warp per 32x32
+// tile (NJ = 4, 248 registers, 8 warps/SM) with one 256-bit load per fragment
+// beats two warps side by side (JS = 2, 16 warps/SM) 64% to 49% of HBM peak.
+static int g_gram_variant = 0;   // debug: 1 = two warps side by side per 32-wide tile (NJ = 2, JS = 2)
 
 static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
     GramPlan p;
     auto frag = [](int64_t v) { return v <= 8 ? 1 : v <= 16 ? 2 : 4; };
     p.ni = frag(k);
-    p.nj = frag(m);
+    if (m > 16 && g_gram_variant == 1) { p.nj = 2; p.js = 2; } else { p.nj = frag(m); p.js = 1; }
     p.tiles_i = (int)((k + 8 * p.ni - 1) / (8 * p.ni));
-    p.tiles_j = (int)((m + 8 * p.nj - 1) / (8 * p.nj));
+    p.tiles_j = (int)((m + 8 * p.nj * p.js - 1) / (8 * p.nj * p.js));
     int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
-    // enough CTAs for ~4 per SM, but at least 64 rows (4 steps) per warp
-    int64_t want = ((int64_t)sm_count() * 4 + tiles - 1) / tiles;
-    int64_t maxc = (n + GRAM_WARPS * 64 - 1) / (GRAM_WARPS * 64);
+    const int64_t step = 16 * (GRAM_WARPS / p.js);          // rows a CTA consumes per step
+    // enough CTAs for ~6 per SM, but at least 4 steps per CTA
+    int64_t want = ((int64_t)sm_count() * 6 + tiles - 1) / tiles;
+    int64_t maxc = (n + 4 * step - 1) / (4 * step);
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
-    int64_t rows_per_cta = (n + want - 1) / want;
-    int64_t rpw = (rows_per_cta + GRAM_WARPS - 1) / GRAM_WARPS;
-    rpw = (rpw + 15) / 16 * 16;
-    p.rows_per_warp = rpw;
-    p.chunks = (int)((n + rpw * GRAM_WARPS - 1) / (rpw * GRAM_WARPS));
+    int64_t rpc = (n + want - 1) / want;
+    rpc = (rpc + step - 1) / step * step;
+    p.rows_per_cta = rpc;
+    p.chunks = (int)((n + rpc - 1) / rpc);
     return p;
 }
 
@@ -66,9 +74,9 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, i
                                       double (&v)[4]) {
     if (ALIGNED) {
         if (active) {
-            double2 a = ldg_stream(reinterpret_cast<const double2*>(p + r));
-            double2 b = ldg_stream(reinterpret_cast<const double2*>(p + r) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+            // one 256-bit load (sm_100): the lane's whole 32-byte sector in a single request
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p + r));
         } else {
             v[0] = v[1] = v[2] = v[3] = 0.0;
         }
@@ -78,14 +86,16 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, i
     }
 }
 
-template <int NI, int NJ>
+template <int NI, int NJ, int JS, bool SAME>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double* __restrict__ O, int64_t ldo,
-                 int k, int64_t n, int64_t rows_per_warp, int fast, double* __restrict__ part) {
-    __shared__ double red[GRAM_WARPS][NI * NJ * 64];
+                 int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part) {
+    constexpr int RW = GRAM_WARPS / JS;              // warps interleaving row steps
+    __shared__ double red[RW][JS * NI * NJ * 64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int jw = warp % JS, rw = warp / JS;
     const int g = lane >> 2, c = lane & 3;
-    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ);
+    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ * JS) + jw * (8 * NJ);
     const int chunk = blockIdx.x;
 
     const double* po[NI];
@@ -102,17 +112,25 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
 #pragma unroll
         for (int b = 0; b < NJ; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    int64_t r_begin = ((int64_t)chunk * GRAM_WARPS + warp) * rows_per_warp;
-    int64_t r_end = r_begin + rows_per_warp < n ? r_begin + rows_per_warp : n;
-    int64_t r = r_begin;
+    const int64_t c_begin = (int64_t)chunk * rows_per_cta;
+    const int64_t c_end = c_begin + rows_per_cta < n ? c_begin + rows_per_cta : n;
+    int64_t r = c_begin + rw * 16;
+    // SAME: X.dot(X) with a single tile -- both operands are the same fragments, load once
     if (fast) {
-        // full 16-row steps with 128-bit loads
-        for (; r + 16 <= r_end; r += 16) {
+        // full 16-row steps, one 256-bit load per fragment
+        for (; r + 16 <= c_end; r += 16 * RW) {
             double fa[NI][4], fb[NJ][4];
 #pragma unroll
             for (int t = 0; t < NI; ++t) load4<true>(po[t], r + 4 * c, n, ai[t], fa[t]);
+            if (SAME) {
 #pragma unroll
-            for (int t = 0; t < NJ; ++t) load4<true>(ps[t], r + 4 * c, n, aj[t], fb[t]);
+                for (int t = 0; t < NJ; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) fb[t][e] = fa[t < NI ? t : 0][e];
+            } else {
+#pragma unroll
+                for (int t = 0; t < NJ; ++t) load4<true>(ps[t], r + 4 * c, n, aj[t], fb[t]);
+            }
 #pragma unroll
             for (int s = 0; s < 4; ++s)
 #pragma unroll
@@ -121,12 +139,12 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
                     for (int b = 0; b < NJ; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a][s], fb[b][s]);
         }
     }
-    for (; r < r_end; r += 16) {   // ragged / unaligned steps
+    for (; r < c_end; r += 16 * RW) {   // ragged / unaligned steps
         double fa[NI][4], fb[NJ][4];
 #pragma unroll
-        for (int t = 0; t < NI; ++t) load4<false>(po[t], r + 4 * c, r_end, ai[t], fa[t]);
+        for (int t = 0; t < NI; ++t) load4<false>(po[t], r + 4 * c, c_end, ai[t], fa[t]);
 #pragma unroll
-        for (int t = 0; t < NJ; ++t) load4<false>(ps[t], r + 4 * c, r_end, aj[t], fb[t]);
+        for (int t = 0; t < NJ; ++t) load4<false>(ps[t], r + 4 * c, c_end, aj[t], fb[t]);
 #pragma unroll
         for (int s = 0; s < 4; ++s)
 #pragma unroll
@@ -140,17 +158,19 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
     for (int a = 0; a < NI; ++a)
 #pragma unroll
         for (int b = 0; b < NJ; ++b) {
-            red[warp][(a * NJ + b) * 64 + g * 8 + 2 * c] = acc[a][b][0];
-            red[warp][(a * NJ + b) * 64 + g * 8 + 2 * c + 1] = acc[a][b][1];
+            red[rw][((jw * NI + a) * NJ + b) * 64 + g * 8 + 2 * c] = acc[a][b][0];
+            red[rw][((jw * NI + a) * NJ + b) * 64 + g * 8 + 2 * c + 1] = acc[a][b][1];
         }
     __syncthreads();
     double* out = part + (int64_t)chunk * k * m;
-    for (int e = threadIdx.x; e < NI * NJ * 64; e += GRAM_THREADS) {
+    const int jbase = blockIdx.y * (8 * NJ * JS);
+    for (int e = threadIdx.x; e < JS * NI * NJ * 64; e += GRAM_THREADS) {
         double v = red[0][e];
 #pragma unroll
-        for (int w = 1; w < GRAM_WARPS; ++w) v += red[w][e];
-        int blk = e >> 6, a = blk / NJ, b = blk % NJ;
-        int i = i0 + 8 * a + ((e & 63) >> 3), j = j0 + 8 * b + (e & 7);
+        for (int w = 1; w < RW; ++w) v += red[w][e];
+        int blk = e >> 6;
+        int b = blk % NJ, a = (blk / NJ) % NI, jj = blk / (NJ * NI);
+        int i = i0 + 8 * a + ((e & 63) >> 3), j = jbase + jj * (8 * NJ) + 8 * b + (e & 7);
         if (i < k && j < m) out[(int64_t)i * m + j] = v;
     }
 }
@@ -250,18 +270,28 @@ template <int NI>
 static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m, const double* O, int64_t ldo,
                           int k, int64_t n, int fast, double* part, cudaStream_t st) {
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
-    switch (p.nj) {
-        case 1: gram_dmma_kernel<NI, 1><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
-        case 2: gram_dmma_kernel<NI, 2><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
-        default: gram_dmma_kernel<NI, 4><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_warp, fast, part); break;
+    const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1 && p.ni == p.nj && p.js == 1;
+#define RL_GRAM_LAUNCH(NJ_, JS_, SAME_) \
+    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part)
+    if (same) {
+        RL_GRAM_LAUNCH(NI, 1, true);
+    } else if (p.nj == 4) {
+        RL_GRAM_LAUNCH(4, 1, false);
+    } else if (p.js == 2) {
+        RL_GRAM_LAUNCH(2, 2, false);
+    } else if (p.nj == 1) {
+        RL_GRAM_LAUNCH(1, 1, false);
+    } else {
+        RL_GRAM_LAUNCH(2, 1, false);
     }
+#undef RL_GRAM_LAUNCH
     return check_launch();
 }
 
 // simt plan: 8x8 tiles
 static GramPlan gram_plan_simt(int64_t m, int64_t k, int64_t n, int vec) {
     GramPlan p;
-    p.ni = p.nj = 1;
+    p.ni = p.nj = p.js = 1;
     p.tiles_i = (int)((k + 7) / 8);
     p.tiles_j = (int)((m + 7) / 8);
     int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
@@ -273,7 +303,7 @@ static GramPlan gram_plan_simt(int64_t m, int64_t k, int64_t n, int vec) {
     int64_t rows_per_cta = (n + want - 1) / want;
     int64_t rpw = (rows_per_cta + GRAM_WARPS - 1) / GRAM_WARPS;
     rpw = (rpw + step - 1) / step * step;
-    p.rows_per_warp = rpw;
+    p.rows_per_cta = rpw;            // rows per WARP for the SIMT kernel
     p.chunks = (int)((n + rpw * GRAM_WARPS - 1) / (rpw * GRAM_WARPS));
     return p;
 }
@@ -287,7 +317,7 @@ extern "C" {
 // gram_mode: 0 = dtype default (fp64 -> DMMA, fp32 -> SIMT fp32 accumulate),
 //            1 = force SIMT, 2 = fp32 data with fp64 accumulation and fp64 output
 static int g_gram_force_simt = 0;
-void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on; }
+void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on & 1; g_gram_variant = (on >> 1) & 1; }
 
 static size_t gram_ws_bytes_impl(int dtype, int64_t m, int64_t k, int64_t n, int acc64) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;
@@ -319,7 +349,8 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
     int chunks;
     if (dtype == RL_F64 && !g_gram_force_simt) {
         GramPlan p = gram_plan(m, k, n);
-        int fast = host_aligned16(s) && host_aligned16(o) && (lds % 2 == 0) && (ldo % 2 == 0);
+        int fast = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 31) == 0 &&
+                   (lds % 4 == 0) && (ldo % 4 == 0);
         const double* S = (const double*)s;
         const double* O = (const double*)o;
         switch (p.ni) {
@@ -338,17 +369,17 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
     unsigned rblocks = (unsigned)((km * 8 + 255) / 256);
     if (dtype == RL_F64) {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 2 == 0) && (ldo % 2 == 0);
-        gram_simt_kernel<double, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const double*)s, lds, (int)m, (const double*)o, ldo, (int)k, n, p.rows_per_warp, fast, (double*)ws);
+        gram_simt_kernel<double, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const double*)s, lds, (int)m, (const double*)o, ldo, (int)k, n, p.rows_per_cta, fast, (double*)ws);
         rc = check_launch(); if (rc) return rc;
         gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
     } else if (acc64) {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
-        gram_simt_kernel<float, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_warp, fast, (double*)ws);
+        gram_simt_kernel<float, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_cta, fast, (double*)ws);
         rc = check_launch(); if (rc) return rc;
         gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
     } else {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
-        gram_simt_kernel<float, float, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_warp, fast, (float*)ws);
+        gram_simt_kernel<float, float, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_cta, fast, (float*)ws);
         rc = check_launch(); if (rc) return rc;
         gram_reduce_kernel<float, float><<<rblocks, 256, 0, st>>>((const float*)ws, km, chunks, (float*)g);
     }

@@ -44,8 +44,8 @@ class SparseSymmetricMatrix:
         self.__indptr = _to_device(indptr)
         self.__indices = _to_device(indices)
         self.__values = _to_device(values)
-        self.__diag = None
         self.__full_diag = full.diagonal()
+        self.__sell = _build_sell32(indptr, indices, values)
 
     def size(self):
         return self.__csr.shape[0]
@@ -74,8 +74,48 @@ class SparseSymmetricMatrix:
         if m < 1:
             return
         y._touch()
+        if self.__sell is not None:
+            sp, sc, sv, nsl = self.__sell
+            check(lib.rl_sell_spmm(self.__code, self.__n, self.__nnz, nsl, sp.ptr, sc.ptr, sv.ptr, x._wptr(), x._ld,
+                                   y._wptr(), y._ld, m, dev.stream()))
+            return
         check(lib.rl_csr_spmm(self.__code, self.__n, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
                               self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, dev.stream()))
+
+    def layout(self):
+        return 'sell32' if self.__sell is not None else 'csr'
+
+
+SELL_MAX_PADDING = 1.5     # use SELL-32 only if it stores at most this many times nnz entries
+
+
+def _build_sell32(indptr, indices, values):
+    """CSR -> SELL-32 on the host (one-off set-up).  Returns device buffers
+    (slice_ptr int64, cols int32, vals) and the slice count, or None when the
+    row lengths are too ragged for the padded layout to pay off."""
+    n = indptr.shape[0] - 1
+    nnz = int(indptr[-1])
+    if n == 0 or nnz == 0:
+        return None
+    lens = numpy.diff(indptr)
+    nsl = (n + 31) // 32
+    padded = numpy.zeros(nsl * 32, dtype=numpy.int64)
+    padded[:n] = lens
+    width = padded.reshape(nsl, 32).max(axis=1)
+    total = int(width.sum()) * 32
+    if total > SELL_MAX_PADDING * nnz + 1024:
+        return None
+    slice_ptr = numpy.zeros(nsl + 1, dtype=numpy.int64)
+    numpy.cumsum(width * 32, out=slice_ptr[1:])
+    rows = numpy.repeat(numpy.arange(n, dtype=numpy.int64), lens)
+    q = numpy.arange(nnz, dtype=numpy.int64) - indptr[rows]
+    dest = slice_ptr[rows // 32] + q * 32 + (rows % 32)
+    cols = numpy.zeros(total, dtype=numpy.int32)
+    # padding entries: val = 0, col = 0 (always a valid column)
+    vals = numpy.zeros(total, dtype=values.dtype)
+    cols[dest] = indices
+    vals[dest] = values
+    return _to_device(slice_ptr), _to_device(cols), _to_device(vals), nsl
 
 
 def _to_device(a):

@@ -37,7 +37,13 @@ def flush_l2():
     _flush.zero_()
 
 
-def timeit(fn, reps=10, warm=3, flush=True):
+REPS = [10]
+
+
+def timeit(fn, reps=None, warm=3, flush=True):
+    reps = reps or REPS[0]
+    if REPS[0] < 3:
+        warm = 1
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -86,6 +92,14 @@ def vec_suite(out, n, m, dtype, only):
         f = lambda: check(lib.rl_gram(code, X._wptr(), X._ld, m, X._wptr(), X._ld, m, n, g.data_ptr(), ws.data_ptr(), wsb, st()))
         ms, best = timeit(f)
         emit(out, 'gram_xx', shape, ms, best, blk, 2.0 * n * m * m)
+        if w == 8 and m > 16:
+            lib.rl_debug_set_gram_simt(2)
+            wsb3 = lib.rl_gram_ws_bytes(code, m, m, n)
+            ws3 = torch.empty(max(wsb3, 16), dtype=torch.uint8, device='cuda')
+            f = lambda: check(lib.rl_gram(code, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.data_ptr(), ws3.data_ptr(), wsb3, st()))
+            ms, best = timeit(f)
+            lib.rl_debug_set_gram_simt(0)
+            emit(out, 'gram_xy_wide', shape, ms, best, 2 * blk, 2.0 * n * m * m, 'one warp per 32x32 tile (A/B)')
         if w == 8:
             lib.rl_debug_set_gram_simt(1)
             wsb2 = lib.rl_gram_ws_bytes(code, m, m, n)
@@ -199,12 +213,19 @@ if __name__ == '__main__':
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--only', default='gram,update,blas1,spmm,gemm,eig')
     ap.add_argument('--out', default='')
+    ap.add_argument('--shape', default='', help='n,m: run the vector suite on this single fp64 shape only')
+    ap.add_argument('--reps', type=int, default=10)
     args = ap.parse_args()
     only = set(args.only.split(','))
+    REPS[0] = args.reps
     out = open(args.out, 'w') if args.out else None
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from oracle import algebra_np as K
     shapes = [(32768, 16), (140874, 32), (2097152, 32)]
+    if args.shape:
+        n_, m_ = (int(t) for t in args.shape.split(','))
+        shapes = [(n_, m_)]
+        args.quick = True
     if not args.quick:
         shapes += [(2097152, 16), (2097152, 64), (2097152, 120), (8388608, 32)]
     for (n, m) in shapes:
