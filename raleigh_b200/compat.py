@@ -54,11 +54,34 @@ class _SlaProxy:
         return self._sla.eigh(*args, **kwargs)
 
 
+class _NumpyProxy:
+    """numpy with eye() accepting the float sizes the reference computes as
+    `min(32, nsv/2)` (partial_svd.py:199-204); NumPy >= 2 rejects them."""
+
+    def __init__(self, np):
+        self._np = np
+
+    def __getattr__(self, name):
+        return getattr(self._np, name)
+
+    def eye(self, n, *args, **kwargs):
+        return self._np.eye(int(n), *args, **kwargs)
+
+
 def shim_scipy():
+    """Version shims the reference needs on ANY backend with current SciPy/NumPy;
+    they touch no algebra."""
+    import numpy
     import scipy.linalg as sla
     import raleigh.core.solver as rsolver
     if not isinstance(rsolver.sla, _SlaProxy):
         rsolver.sla = _SlaProxy(sla)
+    try:
+        import raleigh.interfaces.partial_svd as psvd
+        if not isinstance(psvd.numpy, _NumpyProxy):
+            psvd.numpy = _NumpyProxy(numpy)
+    except ImportError:
+        pass
 
 
 def install(reference_path=None, sparse=True, dense=True):

@@ -29,12 +29,13 @@ from . import device as dev
 
 def _gram64(v):
     """(m, m) fp64 Gram matrix of the selected block, left on the device."""
-    m, n = v.nvec(), v.dimension()
+    m, n = v.nvec(), v.local_dimension()
     wsb = lib.rl_gram_acc64_ws_bytes(v._code, m, m, n)
     ws = dev.Buffer(wsb) if wsb else None
     g = dev.Buffer(m * m * 8)
     check(lib.rl_gram_acc64(v._code, v._wptr(), v._ld, m, v._wptr(), v._ld, m, n, g.ptr,
                             ws.ptr if ws else 0, wsb, dev.stream()))
+    v._reduce_device(g, m * m, numpy.float64)      # row-sharded block: sum the partial Gram matrices
     return g
 
 
@@ -64,7 +65,7 @@ def _host_sym_to_device(a):
 
 def _apply_left(v, coeff, tmp):
     """block <- coeff^T . block  (coeff is (m, m) host fp64) through `tmp`."""
-    m, n = v.nvec(), v.dimension()
+    m, n = v.nvec(), v.local_dimension()
     q = numpy.ascontiguousarray(coeff, dtype=v.data_type())
     v._touch()
     check(lib.rl_update_h(v._code, tmp._wptr(), tmp._ld, m, v._wptr(), v._ld, m, dev.host_ptr(q), m, 1,

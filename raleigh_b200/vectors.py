@@ -42,7 +42,7 @@ class Vectors:
         if isinstance(arg, Vectors):
             first, nv = arg.selected()
             self._set_type(arg.data_type())
-            self._n = arg.dimension()
+            self._n, self._ng, self._shard = arg._n, arg._ng, arg._shard
             self._ld = arg._ld
             if shallow:
                 # NumPy semantics (dense_ndarray.py:55-56): a view of the selected slice
@@ -58,9 +58,9 @@ class Vectors:
         elif isinstance(arg, Matrix):
             if arg.order() != 'C_CONTIGUOUS':
                 raise ValueError('Vectors data must be C_CONTIGUOUS')
-            m, n = arg.shape()
+            m, n = arg._local_shape()
             self._set_type(arg.data_type())
-            self._n = n
+            self._n, self._ng, self._shard = n, n, None     # rows of a (row-sharded) matrix: local vectors
             self._ld = arg._ld
             if shallow:
                 self._buf = arg._buf        # alias the matrix memory (dense_cublas.py:369-376)
@@ -77,15 +77,15 @@ class Vectors:
                 raise ValueError('Vectors data must be a 2D array')
             m, n = arg.shape
             self._set_type(arg.dtype.type)
-            self._n = n
-            self._ld = dev.padded_ld(n, self._w)
+            self._resolve_layout(n)
+            self._ld = dev.padded_ld(self._n, self._w)
             self._alloc(m)
             self._nvec = m
             if m > 0:
-                dev.upload_2d(self._ptr(0), self._ld * self._w, numpy.ascontiguousarray(arg))
+                dev.upload_2d(self._ptr(0), self._ld * self._w, numpy.ascontiguousarray(self._local_part(arg)))
         elif isinstance(arg, numbers.Number):
             self._set_type(numpy.float64 if data_type is None else data_type)
-            self._n = int(arg)
+            self._resolve_layout(int(arg))
             assert nvec >= 0
             self._ld = dev.padded_ld(self._n, self._w)
             self._alloc(int(nvec), zero=True)
@@ -94,6 +94,52 @@ class Vectors:
             raise ValueError('wrong argument %s in constructor' % repr(type(arg)))
         self._sel = (0, self._nvec)
         self._min_inc = Vectors.MIN_INC
+
+    def _resolve_layout(self, n_logical):
+        """Logical (global) dimension -> local length.  A dimension registered with
+        the active ShardContext (dist.py) is row-sharded: this process holds rows
+        [row0, row0 + nloc) and reductions are all-reduced."""
+        from . import dist
+        ctx = dist.current()
+        part = ctx.lookup(n_logical) if ctx is not None else None
+        self._ng = int(n_logical)
+        if part is None:
+            self._n, self._shard = int(n_logical), None
+        else:
+            self._n, self._shard = part[1], (ctx, part[0])
+
+    def _local_part(self, a):
+        """Columns of a host array of logical width that this process owns."""
+        if self._shard is None:
+            return a
+        if a.shape[1] == self._ng:
+            row0 = self._shard[1]
+            return a[:, row0:row0 + self._n]
+        if a.shape[1] == self._n:
+            return a                      # already the local part
+        raise ValueError('array width %d matches neither the global (%d) nor the local (%d) dimension'
+                         % (a.shape[1], self._ng, self._n))
+
+    def _reduce_host(self, a):
+        """Sum a small host result over the ranks that share this sharded block."""
+        if self._shard is None:
+            return a
+        return self._shard[0].allreduce_host(a)
+
+    def _reduce_device(self, buf, count, np_dtype):
+        """All-reduce `count` elements of a device Buffer in place (NCCL over NVLink)."""
+        if self._shard is None:
+            return
+        import torch
+        tdt = torch.float32 if numpy.dtype(np_dtype) == numpy.float32 else torch.float64
+        view = buf.tensor[:count * numpy.dtype(np_dtype).itemsize].view(tdt)
+        self._shard[0].allreduce_(view)
+
+    def is_sharded(self):
+        return self._shard is not None
+
+    def local_dimension(self):
+        return self._n
 
     def _set_type(self, t):
         t = _np_type(t)
@@ -134,11 +180,21 @@ class Vectors:
             return Vectors(self.dimension() if dim is None else dim, int(arg), self.data_type())
         return Vectors(arg)
 
+    @staticmethod
+    def _local(n, nvec, data_type):
+        """Unsharded block whatever the active ShardContext says about `n`."""
+        from . import dist
+        saved, dist._current = dist._current, None
+        try:
+            return Vectors(n, nvec, data_type)
+        finally:
+            dist._current = saved
+
     def clone(self):
         return Vectors(self)
 
     def dimension(self):
-        return self._n
+        return self._ng
 
     def nvec(self):
         return self._sel[1]
@@ -158,6 +214,11 @@ class Vectors:
         (dense_cublas.py:119-131), so that seeded runs reproduce across backends."""
         m, n = self.nvec(), self._n
         if m < 1:
+            return
+        if self._shard is not None:
+            # same seed on every rank (the host RNG streams are identical), rows keyed globally
+            seed = int(numpy.random.randint(0, 2 ** 31 - 1))
+            self.fill_random_device(seed, row0=self._shard[1])
             return
         data = numpy.random.rand(m, n).astype(self._dtype)
         data *= 2
@@ -180,6 +241,8 @@ class Vectors:
         if other.nvec() < 1:
             return
         if axis == 1:
+            if self._shard is not None or other._shard is not None:
+                raise NotImplementedError('append(axis=1) of row-sharded vectors')
             m, n = self.shape()
             l, n_other = other.shape()
             if m != l:
@@ -197,7 +260,7 @@ class Vectors:
             return
         i, m = self.selected()
         j, l = other.selected()
-        if other.dimension() != self._n or other.data_type() != self._dtype:
+        if other._n != self._n or other.data_type() != self._dtype:
             raise ValueError('Cannot append incompatible vectors')
         nvec = i + m + l
         st = dev.stream()
@@ -265,6 +328,15 @@ class Vectors:
         w = numpy.zeros((m,), dtype=self._dtype)
         if m < 1:
             return w
+        if self._shard is not None:
+            wsb = lib.rl_dots_ws_bytes(self._code, m, n)
+            ws = dev.Buffer(wsb) if wsb else None
+            out = dev.Buffer(m * self._w)
+            check(lib.rl_dots(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, n, out.ptr,
+                              ws.ptr if ws else 0, wsb, dev.stream()))
+            self._reduce_device(out, m, self._dtype)
+            check(lib.rl_d2h(dev.host_ptr(w), out.ptr, m * self._w, dev.stream()))
+            return w
         check(lib.rl_dots_h(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, n,
                             dev.host_ptr(w), dev.stream()))
         return w
@@ -276,7 +348,16 @@ class Vectors:
         if m < 1 or k < 1:
             return g
         if max(m, k) > Vectors._GEMM_THRESHOLD:
-            return self._dot_via_gemm(other)
+            return self._reduce_host(self._dot_via_gemm(other))
+        if self._shard is not None:
+            wsb = lib.rl_gram_ws_bytes(self._code, m, k, self._n)
+            ws = dev.Buffer(wsb) if wsb else None
+            out = dev.Buffer(k * m * self._w)
+            check(lib.rl_gram(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, self._n,
+                              out.ptr, ws.ptr if ws else 0, wsb, dev.stream()))
+            self._reduce_device(out, k * m, self._dtype)
+            check(lib.rl_d2h(dev.host_ptr(g), out.ptr, k * m * self._w, dev.stream()))
+            return g
         check(lib.rl_gram_h(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, self._n,
                             dev.host_ptr(g), dev.stream()))
         return g
@@ -286,7 +367,7 @@ class Vectors:
     def _dot_via_gemm(self, other):
         # q (k, m) = other (k, n) . self^T  == Matrix(self).apply(other)
         m, k = self.nvec(), other.nvec()
-        q = Vectors(m, k, self._dtype)
+        q = Vectors._local(m, k, self._dtype)
         check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, self._n, other._wptr(), other._ld,
                                  q._wptr(), q._ld, k, 0, 1.0, 0.0, dev.stream()))
         return q.data()
@@ -347,7 +428,7 @@ class Vectors:
 
     # ------------------------------------------------------------ other methods
     def shape(self):
-        return (self._nvec, self._n)
+        return (self._nvec, self._ng)
 
     def first(self):
         return self._sel[0]
@@ -387,8 +468,9 @@ class Vectors:
         if isinstance(data, numbers.Number):
             data = numpy.full((self.nvec(), self._n), data, dtype=self._dtype)
         m, n = data.shape
-        if m != self.nvec() or n != self._n:
+        if m != self.nvec() or (n != self._ng and n != self._n):
             raise ValueError('mismatching dimensions in fill()')
+        data = self._local_part(data)
         if m < 1:
             return
         if data.dtype.type is not self._dtype:
@@ -397,6 +479,17 @@ class Vectors:
         dev.upload_2d(self._wptr(), self._ld * self._w, numpy.ascontiguousarray(data))
 
     def data(self):
+        m = self.nvec()
+        if m < 1:
+            return numpy.ndarray((m, self._ng), dtype=self._dtype)
+        local = dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
+        if self._shard is None:
+            return local
+        ctx = self._shard[0]
+        return ctx.allgather_columns(local, ctx.allgather_counts(self._n))
+
+    def local_data(self):
+        """The rows of the selected vectors this process owns, (nvec, nloc)."""
         m = self.nvec()
         if m < 1:
             return numpy.ndarray((m, self._n), dtype=self._dtype)
@@ -409,7 +502,7 @@ class Vectors:
         """q = <other, self> (k, m); self -= q^T other; returns q as Vectors
         (k vectors of dimension m).  dense_cublas.py:513-535."""
         m, k, n = self.nvec(), other.nvec(), self._n
-        q = self.new_vectors(k, m)
+        q = Vectors._local(m, k, self._dtype)
         if m < 1 or k < 1:
             return q
         st = dev.stream()
@@ -424,6 +517,7 @@ class Vectors:
             g = dev.Buffer(k * m * self._w)
             check(lib.rl_gram(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, n, g.ptr,
                               ws.ptr if ws else 0, wsb, st))
+            self._reduce_device(g, k * m, self._dtype)
             check(lib.rl_copy(self._code, q._wptr(), q._ld, g.ptr, m, k, m, st))
         check(lib.rl_update(self._code, self._wptr(), self._ld, m, other._wptr(), other._ld, k, q._wptr(),
                             q._ld, 1, -1.0, 1.0, n, st))
@@ -442,8 +536,11 @@ class Matrix:
     """Dense operator holder.  dense_cublas.py:635-776."""
 
     def __init__(self, arg):
+        self._mshard = None                # (ctx, row0) when this process holds a row slab
         if isinstance(arg, Vectors):
             f, m = arg.selected()
+            if arg.is_sharded():
+                raise NotImplementedError('Matrix over row-sharded vectors')
             self._shape = (m, arg.dimension())
             self._dtype = arg.data_type()
             self._order = 'C_CONTIGUOUS'
@@ -470,6 +567,20 @@ class Matrix:
             self._base = 0
             self._buf = dev.Buffer(max(rows, 1) * self._ld * w)
             dev.upload_2d(self._buf.ptr, self._ld * w, stored)
+            from . import dist
+            ctx = dist.current()
+            if ctx is not None and ctx.shard_matrices and ctx.world > 1:
+                # sample-partitioned data matrix: `arg` holds this
+                # rank's rows; the logical shape is the concatenation over ranks
+                if self._order != 'C_CONTIGUOUS':
+                    raise ValueError('a row-sharded Matrix must be C_CONTIGUOUS')
+                counts = ctx.allgather_counts(rows)
+                row0, total = sum(counts[:ctx.rank]), sum(counts)
+                if total == cols:
+                    raise ValueError('square global matrix: sharded and replicated dimensions coincide')
+                ctx.register(total, row0, rows)
+                self._mshard = (ctx, row0)
+                self._shape = (total, cols)
         else:
             raise ValueError('wrong argument %s in Matrix constructor' % repr(type(arg)))
         self._code = _lib.dtype_code(self._dtype)
@@ -479,8 +590,15 @@ class Matrix:
 
     TC_MIN_VECTORS = 8                # below this the FMA-pipe kernel is used
 
-    def _stored_shape(self):
+    def _local_shape(self):
+        """(rows, cols) of the part of the logical matrix held by this process."""
         m, n = self._shape
+        if self._mshard is not None:
+            m = self._mshard[0].lookup(m)[1]
+        return (m, n)
+
+    def _stored_shape(self):
+        m, n = self._local_shape()
         return (m, n) if self._order == 'C_CONTIGUOUS' else (n, m)
 
     def _lo_ptr(self):
@@ -546,11 +664,26 @@ class Matrix:
             raise ValueError('Numbers of input and output vectors differ')
         if k < 1:
             return
+        m, n = self._local_shape()
+        if self._mshard is not None:
+            xs, ys = (x, y) if transp else (y, x)      # xs lives on the sharded (row) dimension
+            if not xs.is_sharded() or xs.local_dimension() != m or ys.is_sharded():
+                raise ValueError('vectors are not laid out like the row-sharded matrix')
         if self._order == 'C_CONTIGUOUS':
             M, N, t = m, n, 1 if transp else 0
         else:   # stored transposed: A = B^T with B (n, m) row-major
             M, N, t = n, m, 0 if transp else 1
         y._touch()
+        self._apply_local(x, y, k, M, N, t)
+        if self._mshard is not None and transp:
+            # partial products of the row slabs -> replicated result (NCCL all-reduce over NVLink)
+            import torch
+            tdt = torch.float32 if self._dtype is numpy.float32 else torch.float64
+            first = (y._off + y._sel[0]) * y._ld * y._w
+            view = y._buf.tensor[first:first + k * y._ld * y._w].view(tdt)
+            self._mshard[0].allreduce_(view)
+
+    def _apply_local(self, x, y, k, M, N, t):
         if (self._dtype is numpy.float32 and k >= Matrix.TC_MIN_VECTORS and
                 lib.rl_dense_apply_tc_supported(self._aptr(), self._ld, x._wptr(), x._ld)):
             wsb = lib.rl_dense_apply_tc_ws_bytes(M, N, k, t)

@@ -1,0 +1,64 @@
+"""Host-side logic of the multi-GPU path with world_size 2 on the gloo backend
+(CPU): partitioning, the sharded-dimension registry and the host collectives the
+Vectors layer uses.  The CUDA kernels themselves are row-local and are covered by
+tests/dist_check.py on >= 2 GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as tdist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    tdist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from raleigh_b200 import dist
+    ctx = dist.enable()
+    assert ctx.world == world and not ctx.on_device
+    n = 1003
+    row0, nloc = ctx.register_even(n)
+    assert ctx.lookup(n) == (row0, nloc) and ctx.lookup(77) is None
+    with pytest.raises(ValueError):
+        ctx.register(n, row0 + 1, nloc)
+    rng = np.random.RandomState(0)
+    x = rng.randn(5, n)
+    y = rng.randn(7, n)
+    xl, yl = x[:, row0:row0 + nloc], y[:, row0:row0 + nloc]
+    g = ctx.allreduce_host(yl @ xl.T)                 # what Vectors.dot does for a sharded block
+    assert np.allclose(g, y @ x.T, atol=1e-10)
+    counts = ctx.allgather_counts(nloc)
+    assert sum(counts) == n and counts[rank] == nloc
+    full = ctx.allgather_columns(xl, counts)          # Vectors.data()
+    assert np.array_equal(full, x)
+    # sample-partitioned dense operator: partial products + all-reduce == global product
+    a = rng.randn(n, 31)
+    al = a[row0:row0 + nloc]
+    z = ctx.allreduce_host(xl @ al)
+    assert np.allclose(z, x @ a, atol=1e-9)
+    out[rank] = 1
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+def test_partition_covers_rows():
+    from raleigh_b200.dist import partition
+    for n, w in ((10, 3), (16777216, 8), (5, 8), (12000, 7)):
+        parts = [partition(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and sum(p[1] for p in parts) == n
+        for a, b in zip(parts, parts[1:]):
+            assert a[0] + a[1] == b[0]
+
+
+def test_shard_context_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert sorted(out.keys()) == [0, 1]
