@@ -50,20 +50,26 @@ def parse():
 
 
 # --------------------------------------------------------------------------- workload
-def generate_c2(rows, cols, rank, device, seed=1):
+def generate_c2(rows, cols, rank, device, seed=1, world=1, shard=0):
     """Synthetic data matrix in the style of the reference's generator
     (examples/pca/generate_matrix.py:55-77 with pca=True, alpha=0.75, plus the
-    --ptb noise, :122-125): A = U diag(k^-0.75) V^T + noise, U[:, 0] = const."""
+    --ptb noise, :122-125): A = U diag(k^-0.75) V^T + noise, U[:, 0] = const.
+    With world > 1 this returns rows [shard*rows, (shard+1)*rows) of the
+    (world*rows) x cols matrix: V is common to all shards, U is drawn per shard
+    and scaled so that its columns stay (nearly) orthonormal globally."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     rank = min(rank, rows, cols)
     sigma = torch.arange(1, rank + 1, device=device, dtype=torch.float32) ** (-0.75)
+    v = torch.randn(cols, rank, generator=g, device=device, dtype=torch.float32)
+    v, _ = torch.linalg.qr(v)
+    g.manual_seed(seed + 7919 * (shard + 1))
     u = torch.randn(rows, rank, generator=g, device=device, dtype=torch.float32)
     u[:, 0] = 1.0
-    v = torch.randn(cols, rank, generator=g, device=device, dtype=torch.float32)
     u, _ = torch.linalg.qr(u)
-    v, _ = torch.linalg.qr(v)
+    if world > 1:
+        u = u / float(world) ** 0.5
     a = (u * sigma[None, :]) @ v.T
     del u, v
     noise = 2 * torch.rand(rows, cols, generator=g, device=device, dtype=torch.float32) - 1
@@ -218,16 +224,26 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world):
     return {'workload': 'C2: PCA of synthetic %dx%d fp32 low-rank+noise (LFW 175x225 shape), %d components, '
-                        'block 128, svtol 1e-3' % (args.rows, args.cols, args.npc),
+                        'block 128, svtol 1e-3%s' % (args.rows * world, args.cols, args.npc,
+                                                     '' if world == 1 else ' (%d rows per GPU)' % args.rows),
             'l2_policy': 'inputs_exceed_l2 (data matrix %.2f GB streamed every operator application)'
                          % (args.rows * args.cols * 4 / 1e9),
-            'parallelism': 'single GPU' if world == 1 else 'replica per GPU (%d)' % world,
+            'parallelism': 'single GPU' if world == 1 else
+            'sample-partitioned data matrix over %d GPUs: row-sharded block vectors, NCCL all-reduce of Gram '
+            'matrices and of the k x n_features partial products' % world,
             'solver': 'reference core solver + lra/partial_svd, unmodified, on raleigh_b200 backend'}
 
 
 def run_b200(args, rank, world, local_rank):
+    """GPU arm.  The host keeps only the solver's k x k algebra (<= 256 x 256), for
+    which multi-threaded BLAS/LAPACK is slower than one thread (SURVEY.md section 6:
+    8 threads were 3x slower than 1 on config 1; torchrun pins OMP_NUM_THREADS=1
+    anyway), so host BLAS is limited to one thread here; the CPU baseline below
+    gets all cores back."""
     import numpy as np
     import torch
+    from threadpoolctl import threadpool_limits
+    host_limit = threadpool_limits(limits=1)
     torch.cuda.set_device(local_rank)
     import raleigh_b200 as rb
     from raleigh_b200 import profile, cuda
@@ -242,15 +258,18 @@ def run_b200(args, rank, world, local_rank):
     from raleigh.algebra.dense_matrix import AMatrix
     from raleigh.core.solver import Options
     import torch.distributed as dist
+    ctx = None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        from raleigh_b200 import dist as rdist
+        ctx = rdist.enable()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    a_dev = generate_c2(args.rows, args.cols, RANK_GEN, 'cuda', seed=1 + rank)
+    a_dev = generate_c2(args.rows, args.cols, RANK_GEN, 'cuda', seed=1, world=world, shard=rank)
     a_pinned = torch.empty((args.rows, args.cols), dtype=torch.float32, pin_memory=True)
     a_pinned.copy_(a_dev)
     a_host = a_pinned.numpy()
@@ -306,6 +325,8 @@ def run_b200(args, rank, world, local_rank):
         res = solve_e2e()
     ms_e2e, res, _, _ = timed(solve_e2e, args.steps)
     mean, trans, comps = res
+    if world > 1:      # `trans` is gathered over ranks: check this rank's rows against its slab
+        trans = trans[rank * args.rows:(rank + 1) * args.rows]
     em, ef = pca_error_gpu(a_dev, mean, trans, comps)
     h2d = a_host.nbytes
     d2h = trans.nbytes + comps.nbytes + mean.nbytes
@@ -333,6 +354,9 @@ def run_b200(args, rank, world, local_rank):
                         'TFLOPs': round(v['TFLOPs'], 2)} for k, v in prof.items()},
         'device_busy_frac': round(sum(v['ms'] for v in prof.values()) / ms_val, 4),
     }
+    if ctx is not None:
+        line['collectives'] = {'allreduce_calls': ctx.allreduce_calls, 'allreduce_MB': round(ctx.allreduce_bytes / 1e6, 1)}
+    host_limit.restore_original_limits()
     if world == 1 and not args.no_cpu_baseline:
         try:
             load_reference_cpu()
