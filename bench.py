@@ -354,6 +354,10 @@ def run_b200(args, rank, world, local_rank):
                         'TFLOPs': round(v['TFLOPs'], 2)} for k, v in prof.items()},
         'device_busy_frac': round(sum(v['ms'] for v in prof.values()) / ms_val, 4),
     }
+    try:
+        line['hbm_kernels'] = hbm_kernel_rates(peaks.get('hbm_gbs') or 6650.0)
+    except Exception as exc:
+        line['hbm_kernels'] = {'error': repr(exc)}
     if ctx is not None:
         line['collectives'] = {'allreduce_calls': ctx.allreduce_calls, 'allreduce_MB': round(ctx.allreduce_bytes / 1e6, 1)}
     host_limit.restore_original_limits()
@@ -368,6 +372,58 @@ def run_b200(args, rank, world, local_rank):
             line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference',
                                     'sample': 'failed: %r' % (exc,)}
     print(json.dumps(line))
+
+
+def hbm_kernel_rates(peak_gbs):
+    """Block-SpMM and Gram bandwidth (the second half of BASELINE.json's metric) on the
+    per-GPU block of config 4 at block size 32: n = 2,097,152 rows (256^3 / 8), fp64,
+    7-point Laplacian slab of 128^3.  CUDA events around the C-ABI calls, L2 flushed
+    between repetitions.  A few milliseconds in total; outside every timed region."""
+    import numpy as np
+    import torch
+    import raleigh_b200 as rb
+    from raleigh_b200._lib import lib, check
+    from raleigh_b200 import device as dev
+    import scipy.sparse as sp
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def timed(fn, reps=5):
+        fn()
+        best = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            best.append(a.elapsed_time(b))
+        best.sort()
+        return best[len(best) // 2]
+
+    out = {}
+    n, m = 2097152, 32
+    X, Y = rb.Vectors(n, m), rb.Vectors(n, m)
+    X.fill_random_device(1)
+    Y.fill_random_device(2)
+    wsb = lib.rl_gram_ws_bytes(1, m, m, n)
+    ws, g = dev.Buffer(wsb), dev.Buffer(m * m * 8)
+    ms = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
+                                         dev.stream())))
+    by = 2.0 * n * m * 8
+    out['gram'] = {'shape': 'n=%d, m=k=%d, fp64' % (n, m), 'ms': ms, 'GBps': by / ms / 1e6,
+                   'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs, 'TFLOPs': 2.0 * n * m * m / ms / 1e9}
+    N = 128
+
+    def lap1(k):
+        return sp.diags([-np.ones(k - 1), 2 * np.ones(k), -np.ones(k - 1)], [-1, 0, 1], format='csr')
+    I = sp.identity(N, format='csr')
+    L = (sp.kron(I, sp.kron(I, lap1(N))) + sp.kron(I, sp.kron(lap1(N), I)) + sp.kron(lap1(N), sp.kron(I, I))).tocsr()
+    A = rb.SparseSymmetricMatrix(L)
+    ms = timed(lambda: A.apply(X, Y))
+    nnz = A.nnz()
+    by = nnz * 12.0 + (n + 1) * 8.0 + 2.0 * n * m * 8
+    out['spmm'] = {'shape': '7-point Laplacian 128^3 (n=%d, nnz=%d), m=%d, fp64, %s' % (n, nnz, m, A.layout()),
+                   'ms': ms, 'GBps': by / ms / 1e6, 'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs}
+    return out
 
 
 def roofline_from(prof, peaks, steps):

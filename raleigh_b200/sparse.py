@@ -87,6 +87,10 @@ class SparseSymmetricMatrix:
 
 
 SELL_MAX_PADDING = 1.5     # use SELL-32 only if it stores at most this many times nnz entries
+SELL_MIN_ROW_NNZ = 24      # ... and rows are long: measured on B200 (profiles/r1c_kernel_tuning.md) the
+                           # staged-CSR kernel wins on stencils (7 nnz/row: 3.7 vs 1.9 TB/s, its 8-vector
+                           # groups keep the gathered lines L1-resident), SELL-32 with 32 accumulators
+                           # wins at 55 nnz/row (0.67 vs 0.38 TB/s, matrix streamed once)
 
 
 def _build_sell32(indptr, indices, values):
@@ -103,7 +107,7 @@ def _build_sell32(indptr, indices, values):
     padded[:n] = lens
     width = padded.reshape(nsl, 32).max(axis=1)
     total = int(width.sum()) * 32
-    if total > SELL_MAX_PADDING * nnz + 1024:
+    if total > SELL_MAX_PADDING * nnz + 1024 or nnz < SELL_MIN_ROW_NNZ * n:
         return None
     slice_ptr = numpy.zeros(nsl + 1, dtype=numpy.int64)
     numpy.cumsum(width * 32, out=slice_ptr[1:])
