@@ -201,6 +201,21 @@ int rl_sell_spmm(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const i
                  const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y,
                  int64_t ldy, int64_t m, void* stream);
 
+/* Row-sharded operator (one process per GPU): the local CSR/SELL holds this rank's
+ * rows with columns renumbered [owned 0..ncols_local) | halo ncols_local..); owned columns
+ * are read from the local block x, halo columns from `halo`, the buffer received from the
+ * peers, ROW-INTERLEAVED: halo[(c - ncols_local)*m + v].  rl_pack_rows builds the matching
+ * send buffer out[t*m + v] = x[v, idx[t]] (idx on the device).  The exchange itself is an
+ * NCCL all-to-all driven from the host side (raleigh_b200/sparse.py). */
+int rl_pack_rows(int dtype, const void* x, int64_t ldx, int64_t m, const int64_t* idx, int64_t count,
+                 void* out, void* stream);
+int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                     int64_t ncols_local, const void* halo, void* stream);
+int rl_sell_spmm_halo(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const int64_t* slice_ptr,
+                      const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y,
+                      int64_t ldy, int64_t m, int64_t ncols_local, const void* halo, void* stream);
+
 /* ---- small dense algebra on device (no host LAPACK) ----------------------- */
 /* Symmetric eigen-decomposition of the (p, p) row-major matrix `a` (fp64) by
  * cyclic Jacobi rotations: on return w[0..p) ascending eigenvalues and a holds

@@ -75,6 +75,11 @@ PROTOTYPES = {
                                   c_dbl, c_dbl, c_vp, c_sz, c_vp]),
     'rl_csr_spmm': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     'rl_sell_spmm': (c_int, [c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    'rl_pack_rows': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    'rl_csr_spmm_halo': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                 c_vp]),
+    'rl_sell_spmm_halo': (c_int, [c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64,
+                                  c_vp, c_vp]),
     'rl_syevj_ws_bytes': (c_sz, [c_i64]),
     'rl_syevj': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, ctypes.POINTER(c_int), c_vp]),
 }

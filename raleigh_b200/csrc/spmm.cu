@@ -18,11 +18,21 @@ namespace rl {
 
 constexpr int SPMM_WARPS = 4;
 
+// Column c of the operator: owned columns come from the local block X (vector-major),
+// halo columns (c >= ncols_local, row-sharded operator) from the exchanged halo buffer H,
+// which is row-interleaved: H[(c - ncols_local) * m + v].
+template <typename T>
+__device__ __forceinline__ T xval(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H, int m,
+                                  int ncols_local, int v, int c) {
+    return (H == nullptr || c < ncols_local) ? __ldg(X + (int64_t)v * ldx + c)
+                                             : __ldg(H + (int64_t)(c - ncols_local) * m + v);
+}
+
 template <typename T, int VG>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
-            int m, int cap) {
+            int m, int cap, int ncols_local, const T* __restrict__ H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* sval = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap;
@@ -52,7 +62,6 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
         T acc[VG];
 #pragma unroll
         for (int g = 0; g < VG; ++g) acc[g] = T(0);
-        const T* xb = X + (int64_t)v0 * ldx;
         const int nv = m - v0 < VG ? m - v0 : VG;
         if (staged) {
             if (nv == VG) {
@@ -62,7 +71,10 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
                     const T a0 = sval[p], a1 = sval[p + 1];
                     T x0[VG], x1[VG];
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) { x0[g] = __ldg(xb + (int64_t)g * ldx + c0); x1[g] = __ldg(xb + (int64_t)g * ldx + c1); }
+                    for (int g = 0; g < VG; ++g) {
+                        x0[g] = xval(X, ldx, H, m, ncols_local, v0 + g, c0);
+                        x1[g] = xval(X, ldx, H, m, ncols_local, v0 + g, c1);
+                    }
 #pragma unroll
                     for (int g = 0; g < VG; ++g) { acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]); }
                 }
@@ -70,7 +82,7 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
                     const int c0 = scol[p];
                     const T a0 = sval[p];
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                    for (int g = 0; g < VG; ++g) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
                 }
             } else {
                 for (int p = q0; p < q1; ++p) {
@@ -78,7 +90,7 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
                     const T a0 = sval[p];
 #pragma unroll
                     for (int g = 0; g < VG; ++g)
-                        if (g < nv) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                        if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
                 }
             }
         } else {
@@ -87,7 +99,7 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
                 const T a0 = __ldg(values + p);
 #pragma unroll
                 for (int g = 0; g < VG; ++g)
-                    if (g < nv) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                    if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
             }
         }
         if (live) {
@@ -100,7 +112,8 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
 
 template <typename T>
 static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
-                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, cudaStream_t st) {
+                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
+                     cudaStream_t st) {
     // shared-memory capacity per warp: twice the average entries of 32 rows,
     // rounded to a power of two in [256, 4096]
     int64_t avg = nrows > 0 ? (nnz * 32 + nrows - 1) / nrows : 0;
@@ -116,7 +129,7 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     }
     int64_t blocks = (nrows + SPMM_WARPS * 32 - 1) / (SPMM_WARPS * 32);
     kern<<<(unsigned)blocks, SPMM_WARPS * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
-                                                          (T*)y, ldy, (int)m, cap);
+                                                          (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
     return check_launch();
 }
 
@@ -131,13 +144,12 @@ template <typename T, int MT>
 __global__ void __launch_bounds__(128)
 sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ cols, const T* __restrict__ vals, const T* __restrict__ X, int64_t ldx,
-                 T* __restrict__ Y, int64_t ldy, int v0, int nv) {
+                 T* __restrict__ Y, int64_t ldy, int v0, int nv, int m, int ncols_local, const T* __restrict__ H) {
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (s >= nslices) return;
     const int64_t r = s * 32 + lane;
     const int64_t b0 = __ldg(slice_ptr + s), b1 = __ldg(slice_ptr + s + 1);
-    const T* xb = X + (int64_t)v0 * ldx;
     T acc[MT];
 #pragma unroll
     for (int g = 0; g < MT; ++g) acc[g] = T(0);
@@ -148,15 +160,15 @@ sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ sli
             const T a0 = __ldg(vals + p), a1 = __ldg(vals + p + 32);
 #pragma unroll
             for (int g = 0; g < MT; ++g) {
-                acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
-                acc[g] = fma(a1, __ldg(xb + (int64_t)g * ldx + c1), acc[g]);
+                acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
+                acc[g] = fma(a1, xval(X, ldx, H, m, ncols_local, v0 + g, c1), acc[g]);
             }
         }
         if (p < b1) {
             const int c0 = __ldg(cols + p);
             const T a0 = __ldg(vals + p);
 #pragma unroll
-            for (int g = 0; g < MT; ++g) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+            for (int g = 0; g < MT; ++g) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
         }
     } else {
         for (; p < b1; p += 32) {
@@ -164,7 +176,7 @@ sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ sli
             const T a0 = __ldg(vals + p);
 #pragma unroll
             for (int g = 0; g < MT; ++g)
-                if (g < nv) acc[g] = fma(a0, __ldg(xb + (int64_t)g * ldx + c0), acc[g]);
+                if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
         }
     }
     if (r < nrows) {
@@ -176,20 +188,21 @@ sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ sli
 
 template <typename T>
 static int sell_impl(int64_t nrows, int64_t nslices, const int64_t* slice_ptr, const int32_t* cols, const void* vals,
-                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, cudaStream_t st) {
+                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
+                     cudaStream_t st) {
     const unsigned blocks = (unsigned)((nslices + 3) / 4);
     for (int64_t v0 = 0; v0 < m;) {
         const int64_t left = m - v0;
         int rc;
         if (left > 16) {
             const int nv = left < 32 ? (int)left : 32;
-            sell_spmm_kernel<T, 32><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, nv);
+            sell_spmm_kernel<T, 32><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, nv, (int)m, ncols_local, (const T*)halo);
             v0 += nv;
         } else if (left > 8) {
-            sell_spmm_kernel<T, 16><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left);
+            sell_spmm_kernel<T, 16><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
             v0 += left;
         } else {
-            sell_spmm_kernel<T, 8><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left);
+            sell_spmm_kernel<T, 8><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
             v0 += left;
         }
         rc = check_launch();
@@ -198,37 +211,81 @@ static int sell_impl(int64_t nrows, int64_t nslices, const int64_t* slice_ptr, c
     return 0;
 }
 
+// Halo packing for the row-sharded operator: out[t*m + v] = X[v, idx[t]]
+// (row-interleaved, so that the rows requested by one peer are contiguous).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const T* __restrict__ X, int64_t ldx, int m, const int64_t* __restrict__ idx, int64_t count,
+                 T* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count * m) return;
+    const int64_t t = e / m;
+    const int v = (int)(e - t * m);
+    out[e] = __ldg(X + (int64_t)v * ldx + __ldg(idx + t));
+}
+
 }  // namespace rl
 
 using namespace rl;
 
 extern "C" {
 
+int rl_pack_rows(int dtype, const void* x, int64_t ldx, int64_t m, const int64_t* idx, int64_t count, void* out,
+                 void* stream) {
+    if (m < 0 || count < 0 || m > INT32_MAX) return RL_E_ARG;
+    if (m == 0 || count == 0) return 0;
+    const unsigned blocks = (unsigned)((count * m + 255) / 256);
+    if (dtype == RL_F32) pack_rows_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)x, ldx, (int)m, idx, count, (float*)out);
+    else if (dtype == RL_F64) pack_rows_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>((const double*)x, ldx, (int)m, idx, count, (double*)out);
+    else return RL_E_DTYPE;
+    return check_launch();
+}
+
+int rl_sell_spmm_halo(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const int64_t* slice_ptr,
+                      const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y, int64_t ldy,
+                      int64_t m, int64_t ncols_local, const void* halo, void* stream);
+
 int rl_sell_spmm(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const int64_t* slice_ptr,
                  const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
                  void* stream) {
-    if (nrows < 0 || m < 0 || nnz < 0 || nslices < 0 || m > INT32_MAX) return RL_E_ARG;
+    return rl_sell_spmm_halo(dtype, nrows, nnz, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, 0, nullptr, stream);
+}
+
+int rl_sell_spmm_halo(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, const int64_t* slice_ptr,
+                      const int32_t* cols, const void* vals, const void* x, int64_t ldx, void* y, int64_t ldy,
+                      int64_t m, int64_t ncols_local, const void* halo, void* stream) {
+    if (nrows < 0 || m < 0 || nnz < 0 || nslices < 0 || m > INT32_MAX || ncols_local > INT32_MAX) return RL_E_ARG;
     if (nrows == 0 || m == 0) return 0;
     if (x == y) return RL_E_ALIAS;
     const double w = dtype == RL_F32 ? 4.0 : 8.0;
     // algorithmic traffic is that of the unpadded matrix
     Span span(PK_SPMM, as_stream(stream), nnz * (w + 4.0) + (nrows + 1) * 8.0 + 2.0 * nrows * m * w,
               2.0 * nnz * m);
-    if (dtype == RL_F32) return sell_impl<float>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, as_stream(stream));
-    if (dtype == RL_F64) return sell_impl<double>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, as_stream(stream));
+    if (dtype == RL_F32) return sell_impl<float>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
+    if (dtype == RL_F64) return sell_impl<double>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
     return RL_E_DTYPE;
 }
 
+int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                     int64_t ncols_local, const void* halo, void* stream);
+
 int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                 const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, void* stream) {
-    if (nrows < 0 || m < 0 || nnz < 0 || m > INT32_MAX) return RL_E_ARG;
+    return rl_csr_spmm_halo(dtype, nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, 0, nullptr, stream);
+}
+
+int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                     int64_t ncols_local, const void* halo, void* stream) {
+    if (nrows < 0 || m < 0 || nnz < 0 || m > INT32_MAX || ncols_local > INT32_MAX) return RL_E_ARG;
     if (nrows == 0 || m == 0) return 0;
     if (x == y) return RL_E_ALIAS;
     const double w = dtype == RL_F32 ? 4.0 : 8.0;
     Span span(PK_SPMM, as_stream(stream), nnz * (w + 4.0) + (nrows + 1) * 8.0 + 2.0 * nrows * m * w,
               2.0 * nnz * m);
-    if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
-    if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, as_stream(stream));
+    if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
+    if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
     return RL_E_DTYPE;
 }
 

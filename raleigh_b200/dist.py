@@ -94,6 +94,66 @@ class ShardContext:
         tdist.barrier(group=self.group)
 
 
+class HaloPlan:
+    """Communication plan of a row-partitioned sparse operator.
+
+    Input: this rank's rows of the full operator as CSR with GLOBAL column indices and
+    the contiguous row partition.  Output: the local matrix with columns renumbered
+    [owned 0..nloc) | halo nloc..nloc+nhalo), halo columns ordered by owner rank and
+    then by global index; for every peer the local rows it needs from us (`send_idx`,
+    concatenated in peer order, `send_counts`) and how many halo rows arrive from each
+    peer (`recv_counts`).  Per SpMM only those boundary rows cross NVLink."""
+
+    def __init__(self, ctx, indptr, indices, row0, nloc, n_global):
+        self.ctx = ctx
+        world, rank = ctx.world, ctx.rank
+        starts = numpy.array([partition(n_global, world, r)[0] for r in range(world)] + [n_global], dtype=numpy.int64)
+        assert starts[rank] == row0 and starts[rank + 1] - row0 == nloc
+        indices = numpy.asarray(indices, dtype=numpy.int64)
+        owned = (indices >= row0) & (indices < row0 + nloc)
+        halo_cols = numpy.unique(indices[~owned])                    # sorted global ids => grouped by owner
+        owner = numpy.searchsorted(starts, halo_cols, side='right') - 1
+        self.recv_counts = [int(numpy.count_nonzero(owner == r)) for r in range(world)]
+        self.nhalo = int(halo_cols.shape[0])
+        self.nloc = int(nloc)
+        local = numpy.empty_like(indices)
+        local[owned] = indices[owned] - row0
+        local[~owned] = nloc + numpy.searchsorted(halo_cols, indices[~owned])
+        self.local_indices = local.astype(numpy.int32)
+        self.indptr = numpy.asarray(indptr, dtype=numpy.int64)
+        # tell every owner which of its rows we need
+        need = [halo_cols[owner == r] - starts[r] for r in range(world)]
+        wanted = self._exchange_lists(need)
+        self.send_counts = [int(w.shape[0]) for w in wanted]
+        self.send_idx = numpy.concatenate(wanted).astype(numpy.int64) if world > 0 else numpy.zeros(0, numpy.int64)
+
+    def _exchange_lists(self, need):
+        world = self.ctx.world
+        gathered = [None] * world
+        tdist.all_gather_object(gathered, [numpy.asarray(a, dtype=numpy.int64) for a in need], group=self.ctx.group)
+        return [numpy.asarray(gathered[src][self.ctx.rank], dtype=numpy.int64) for src in range(world)]
+
+    def exchange(self, send, recv, m):
+        """send: torch tensor (sum(send_counts) * m,), recv: (nhalo * m,), both grouped by peer."""
+        ctx = self.ctx
+        ins = [c * m for c in self.send_counts]
+        outs = [c * m for c in self.recv_counts]
+        if ctx.on_device:
+            tdist.all_to_all_single(recv, send, output_split_sizes=outs, input_split_sizes=ins, group=ctx.group)
+            return
+        ops, so, ro = [], 0, 0
+        for peer in range(ctx.world):
+            if ins[peer]:
+                ops.append(tdist.P2POp(tdist.isend, send[so:so + ins[peer]], peer, group=ctx.group))
+            if outs[peer]:
+                ops.append(tdist.P2POp(tdist.irecv, recv[ro:ro + outs[peer]], peer, group=ctx.group))
+            so += ins[peer]
+            ro += outs[peer]
+        if ops:
+            for req in tdist.batch_isend_irecv(ops):
+                req.wait()
+
+
 def enable(group=None, shard_matrices=True):
     """Activate sharding for objects created from now on in this process."""
     global _current

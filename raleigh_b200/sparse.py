@@ -24,34 +24,70 @@ class SparseSymmetricMatrix:
     that one gather-only SpMM kernel serves it; building it is one-off host
     set-up, like the reference's own `triu` + `sort_indices`."""
 
-    def __init__(self, matrix):
-        try:
-            csr = matrix.csr()
-        except Exception:
-            csr = scs.triu(matrix, format='csr')
-            csr.sort_indices()
+    def __init__(self, matrix, local_rows=None):
+        """`matrix`: SciPy sparse matrix (or another SparseSymmetricMatrix), as in the
+        reference.  Under an active ShardContext (dist.enable()) the operator is
+        row-partitioned: every rank keeps the rows of its slab; pass
+        `local_rows=(row0, n_global)` together with a (nloc, n_global) matrix holding
+        just those rows of the FULL symmetric operator to avoid ever forming the
+        global matrix (config 4 generates its slabs this way)."""
+        from . import dist
+        ctx = dist.current()
+        self.__plan = None
+        if local_rows is not None:
+            if ctx is None:
+                raise ValueError('local_rows needs an active ShardContext')
+            row0, n_global = int(local_rows[0]), int(local_rows[1])
+            slab = matrix.tocsr()
+            slab.sort_indices()
+            csr = None
+            self.__n = n_global
+        else:
+            try:
+                csr = matrix.csr()
+            except Exception:
+                csr = scs.triu(matrix, format='csr')
+                csr.sort_indices()
+            strict = scs.triu(csr, k=1, format='csr')
+            full = (csr + strict.T).tocsr()
+            full.sort_indices()
+            self.__n = csr.shape[0]
+            slab = full
+            if ctx is not None and ctx.shard_matrices and ctx.world > 1:
+                row0, nloc = dist.partition(self.__n, ctx.world, ctx.rank)
+                slab = full[row0:row0 + nloc].tocsr()
+                slab.sort_indices()
         self.__csr = csr
-        dtype = csr.data.dtype.type
+        dtype = slab.data.dtype.type
+        self.__dtype = slab.data.dtype
         self.__code = _lib.dtype_code(dtype)          # raises ValueError for complex
-        strict = scs.triu(csr, k=1, format='csr')
-        full = (csr + strict.T).tocsr()
-        full.sort_indices()
-        self.__n = csr.shape[0]
-        self.__nnz = int(full.nnz)
+        self.__nnz = int(slab.nnz)
+        self.__nrows = slab.shape[0]
+        if ctx is not None and ctx.shard_matrices and ctx.world > 1:
+            nloc = slab.shape[0]
+            if local_rows is None:
+                row0 = dist.partition(self.__n, ctx.world, ctx.rank)[0]
+            ctx.register(self.__n, row0, nloc)
+            self.__plan = dist.HaloPlan(ctx, slab.indptr, slab.indices, row0, nloc, self.__n)
+            self.__send_idx = _to_device(self.__plan.send_idx)
+            self.__full_diag = numpy.asarray(slab[:, row0:row0 + nloc].diagonal())
+            full = scs.csr_matrix((slab.data, self.__plan.local_indices, slab.indptr),
+                                  shape=(nloc, nloc + self.__plan.nhalo))
         indptr = numpy.ascontiguousarray(full.indptr, dtype=numpy.int64)
         indices = numpy.ascontiguousarray(full.indices, dtype=numpy.int32)
         values = numpy.ascontiguousarray(full.data, dtype=dtype)
         self.__indptr = _to_device(indptr)
         self.__indices = _to_device(indices)
         self.__values = _to_device(values)
-        self.__full_diag = full.diagonal()
+        if self.__plan is None:
+            self.__full_diag = full.diagonal()
         self.__sell = _build_sell32(indptr, indices, values)
 
     def size(self):
-        return self.__csr.shape[0]
+        return self.__n
 
     def data_type(self):
-        return self.__csr.data.dtype
+        return self.__dtype
 
     def csr(self):
         return self.__csr
@@ -71,16 +107,40 @@ class SparseSymmetricMatrix:
             raise ValueError('Numbers of input and output vectors differ')
         if x.dimension() != self.__n or y.dimension() != self.__n:
             raise ValueError('Matrix and vectors dimensions incompatible')
+        if x.data_type() != self.__dtype.type or y.data_type() != self.__dtype.type:
+            raise ValueError('Matrix and vectors data types differ')
         if m < 1:
             return
         y._touch()
+        ncl, halo = 0, 0
+        if self.__plan is not None:
+            if not (x.is_sharded() and y.is_sharded() and x.local_dimension() == self.__nrows):
+                raise ValueError('vectors are not laid out like the row-sharded operator')
+            ncl, halo = self.__nrows, self._exchange_halo(x, m)
         if self.__sell is not None:
             sp, sc, sv, nsl = self.__sell
-            check(lib.rl_sell_spmm(self.__code, self.__n, self.__nnz, nsl, sp.ptr, sc.ptr, sv.ptr, x._wptr(), x._ld,
-                                   y._wptr(), y._ld, m, dev.stream()))
+            check(lib.rl_sell_spmm_halo(self.__code, self.__nrows, self.__nnz, nsl, sp.ptr, sc.ptr, sv.ptr,
+                                        x._wptr(), x._ld, y._wptr(), y._ld, m, ncl, halo, dev.stream()))
             return
-        check(lib.rl_csr_spmm(self.__code, self.__n, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
-                              self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, dev.stream()))
+        check(lib.rl_csr_spmm_halo(self.__code, self.__nrows, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
+                                   self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, ncl, halo, dev.stream()))
+
+    def _exchange_halo(self, x, m):
+        """Pack the boundary rows every peer needs (kernel), all-to-all over NVLink
+        (NCCL), return the device address of the received row-interleaved halo."""
+        import torch
+        plan = self.__plan
+        tdt = torch.float32 if x.data_type() is numpy.float32 else torch.float64
+        nsend = int(plan.send_idx.shape[0])
+        send = torch.empty(max(nsend * m, 1), dtype=tdt, device='cuda')
+        recv = torch.empty(max(plan.nhalo * m, 1), dtype=tdt, device='cuda')
+        if nsend:
+            check(lib.rl_pack_rows(x._code, x._wptr(), x._ld, m, self.__send_idx.ptr, nsend, send.data_ptr(),
+                                   dev.stream()))
+        plan.exchange(send[:nsend * m], recv[:plan.nhalo * m], m)
+        self.__halo_keepalive = (send, recv)
+        self.halo_bytes = getattr(self, 'halo_bytes', 0) + (nsend + plan.nhalo) * m * x.data_size()
+        return recv.data_ptr()
 
     def layout(self):
         return 'sell32' if self.__sell is not None else 'csr'
@@ -146,10 +206,15 @@ class DiagonalPreconditioner:
         self.__inv = 1.0 / numpy.asarray(d)
         self.__dev = {}
 
-    def _inv_on_device(self, dtype):
-        key = numpy.dtype(dtype).type
+    def _inv_on_device(self, dtype, x=None):
+        key = (numpy.dtype(dtype).type, 0, self.__inv.shape[0])
+        inv = self.__inv
+        if x is not None and x.is_sharded() and inv.shape[0] == x.dimension() != x.local_dimension():
+            row0 = x._shard[1]                      # diagonal given globally: keep this rank's rows
+            key = (key[0], row0, x.local_dimension())
+            inv = inv[row0:row0 + x.local_dimension()]
         if key not in self.__dev:
-            self.__dev[key] = _to_device(numpy.ascontiguousarray(self.__inv, dtype=key))
+            self.__dev[key] = _to_device(numpy.ascontiguousarray(inv, dtype=key[0]))
         return self.__dev[key]
 
     def apply(self, x, y):
@@ -157,9 +222,9 @@ class DiagonalPreconditioner:
             m = x.nvec()
             if m < 1:
                 return
-            d = self._inv_on_device(x.data_type())
+            d = self._inv_on_device(x.data_type(), x)
             y._touch()
-            check(lib.rl_diag_mul(x._code, y._wptr(), y._ld, x._wptr(), x._ld, m, x.dimension(), d.ptr,
+            check(lib.rl_diag_mul(x._code, y._wptr(), y._ld, x._wptr(), x._ld, m, x.local_dimension(), d.ptr,
                                   dev.stream()))
         else:
             y[...] = x * self.__inv[None, :].astype(x.dtype)

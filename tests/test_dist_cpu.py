@@ -41,6 +41,31 @@ def _worker(rank, world, port, out):
     al = a[row0:row0 + nloc]
     z = ctx.allreduce_host(xl @ al)
     assert np.allclose(z, x @ a, atol=1e-9)
+    # halo plan of a row-partitioned sparse operator: pack -> exchange -> local product
+    import scipy.sparse as sp
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from oracle import algebra_np as K
+    L = K.lap3d_csr(7, 6, 5)
+    R = sp.random(210, 210, density=0.03, random_state=4, format='csr')
+    for A in (L, (L + R + R.T).tocsr()):
+        ng = A.shape[0]
+        r0, nl = dist.partition(ng, world, rank)
+        slab = A[r0:r0 + nl].tocsr()
+        slab.sort_indices()
+        plan = dist.HaloPlan(ctx, slab.indptr, slab.indices, r0, nl, ng)
+        assert sum(plan.recv_counts) == plan.nhalo and plan.recv_counts[rank] == 0 and plan.send_counts[rank] == 0
+        xg = rng.randn(3, ng)
+        xloc = xg[:, r0:r0 + nl]
+        m = 3
+        send = torch.from_numpy(np.ascontiguousarray(xloc[:, plan.send_idx].T).reshape(-1))   # row-interleaved pack
+        recv = torch.empty(plan.nhalo * m, dtype=torch.float64)
+        plan.exchange(send, recv, m)
+        halo = recv.numpy().reshape(plan.nhalo, m).T                                          # (m, nhalo)
+        xext = np.concatenate([xloc, halo], axis=1)
+        Aloc = sp.csr_matrix((slab.data, plan.local_indices, plan.indptr), shape=(nl, nl + plan.nhalo))
+        yloc = (Aloc @ xext.T).T
+        assert np.allclose(yloc, (A @ xg.T).T[:, r0:r0 + nl], atol=1e-9)
     out[rank] = 1
     tdist.barrier()
     tdist.destroy_process_group()
