@@ -141,8 +141,10 @@ size_t rl_gram_acc64_ws_bytes(int dtype, int64_t m, int64_t k, int64_t n);
 int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* o,
                   int64_t ldo, int64_t k, int64_t n, double* g, void* ws,
                   size_t ws_bytes, void* stream);
-/* test hook: non-zero forces the FMA-pipe Gram kernel for fp64 (A/B runs) */
+/* test hooks for A/B runs: bit 0 forces the FMA-pipe Gram kernel for fp64, bit 1 the
+ * two-warps-per-tile DMMA variant; rl_debug_set_update_fma forces the FMA-pipe update */
 void rl_debug_set_gram_simt(int on);
+void rl_debug_set_update_fma(int on);
 /* Vectors.multiply(q, out) dense_cublas.py:271-299 (gemm, beta=0) and
  * Vectors.add(other, s, q) dense_cublas.py:317-342 (gemm, beta=1):
  * Out[j,:] = beta*Out[j,:] + alpha * sum_{i<k} Q[i*q_rs + j*q_cs] * X[i,:], j < m.

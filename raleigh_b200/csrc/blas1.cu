@@ -511,7 +511,7 @@ size_t rl_dots_ws_bytes(int dtype, int64_t m, int64_t n) {
 int rl_dots(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo, int64_t m, int64_t n, void* w,
             void* ws, size_t ws_bytes, void* stream) {
     if (m < 0 || n < 0) return RL_E_ARG;
-    Span span(PK_DOTS, as_stream(stream), 2.0 * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
+    Span span(PK_DOTS, as_stream(stream), (s == o ? 1.0 : 2.0) * m * n * (dtype == RL_F32 ? 4 : 8), 2.0 * m * n);
     RL_DISPATCH(dtype, { return dots_impl<T>(s, lds, o, ldo, m, n, w, ws, ws_bytes, as_stream(stream)); })
 }
 

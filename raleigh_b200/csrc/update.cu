@@ -126,6 +126,183 @@ update_kernel(T* __restrict__ Out, int64_t ldo, int m, const T* __restrict__ X, 
     }
 }
 
+// ---- fp64 tensor-pipe variant ----------------------------------------------------
+// D(j, r) = sum_i Q[i, j] X[i, r] as DMMA m8n8k4 with A = Q^T (from shared memory) and
+// B = X straight from global memory: lane (g, c) reads the four consecutive rows
+// R+4g..R+4g+3 of vector i0+c with ONE 256-bit load and feeds them to four n-tiles, so a
+// warp step covers 32 rows x 4 input vectors with 4 fully used 256-byte requests.  The
+// C fragments of the four n-tiles give each lane 8 consecutive rows of one output
+// vector: two 256-bit stores.  No per-FMA shared-memory traffic (the FMA-pipe kernel
+// above is co-limited by LDS, fp64 pipe and DRAM at m = k = 32, profiles/r1b_gram_ncu.md).
+constexpr int UD_WARPS = 4;
+constexpr int UD_JB = 32;            // outputs per CTA
+constexpr int UD_KMAX = 512;
+
+__device__ __forceinline__ void ud_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void ld256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld256_rw(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(UD_WARPS * 32)
+update_dmma_kernel(double* __restrict__ Out, int64_t ldo, int m, const double* __restrict__ X, int64_t ldx, int k,
+                   const double* __restrict__ Q, int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n,
+                   int kp, int64_t blocks_per_cta) {
+    extern __shared__ __align__(16) double Qs[];          // [UD_JB][kp], kp = 4 mod 16: i contiguous
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int j_base = blockIdx.y * UD_JB;
+    const int ksteps = (k + 3) >> 2;
+    for (int e = threadIdx.x; e < UD_JB * kp; e += UD_WARPS * 32) {
+        const int jj = e / kp, ii = e - jj * kp;
+        const int j = j_base + jj;
+        Qs[e] = (ii < k && j < m) ? alpha * __ldg(Q + (int64_t)ii * q_rs + (int64_t)j * q_cs) : 0.0;
+    }
+    __syncthreads();
+
+    const int64_t nblocks = (n + 31) >> 5;                // 32-row blocks
+    const int64_t b_begin = (int64_t)blockIdx.x * blocks_per_cta;
+    const int64_t b_end = b_begin + blocks_per_cta < nblocks ? b_begin + blocks_per_cta : nblocks;
+    for (int64_t blk = b_begin + warp; blk < b_end; blk += UD_WARPS) {
+        const int64_t R = blk << 5;
+        const bool full = R + 32 <= n;
+        double acc[NJ][4][2];
+#pragma unroll
+        for (int t = 0; t < NJ; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+        const double* px = X + R + 4 * g;
+        if (full) {
+            int ks = 0;
+            for (; ks + 4 <= ksteps; ks += 4) {            // 4 k-steps = 16 input vectors, 4 loads in flight
+                double xb[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = 4 * (ks + q) + c;
+                    if (i < k) ld256(px + (int64_t)i * ldx, xb[q]);
+                    else xb[q][0] = xb[q][1] = xb[q][2] = xb[q][3] = 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int t = 0; t < NJ; ++t) {
+                        const double a = Qs[(8 * t + g) * kp + 4 * (ks + q) + c];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) ud_dmma(acc[t][u][0], acc[t][u][1], a, xb[q][u]);
+                    }
+                }
+            }
+            for (; ks < ksteps; ++ks) {
+                double xb[4];
+                const int i = 4 * ks + c;
+                if (i < k) ld256(px + (int64_t)i * ldx, xb);
+                else xb[0] = xb[1] = xb[2] = xb[3] = 0.0;
+#pragma unroll
+                for (int t = 0; t < NJ; ++t) {
+                    const double a = Qs[(8 * t + g) * kp + 4 * ks + c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ud_dmma(acc[t][u][0], acc[t][u][1], a, xb[u]);
+                }
+            }
+        } else {
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double xb[4];
+                const int i = 4 * ks + c;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t r = R + 4 * g + u;
+                    xb[u] = (i < k && r < n) ? __ldg(X + (int64_t)i * ldx + r) : 0.0;
+                }
+#pragma unroll
+                for (int t = 0; t < NJ; ++t) {
+                    const double a = Qs[(8 * t + g) * kp + 4 * ks + c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ud_dmma(acc[t][u][0], acc[t][u][1], a, xb[u]);
+                }
+            }
+        }
+        // n-tile u, C fragment (g, c): output vector j = 8t+g, rows R + 4*(2c) + u and R + 4*(2c+1) + u
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) {
+            const int j = j_base + 8 * t + g;
+            if (j >= m) continue;
+            double* po = Out + (int64_t)j * ldo + R + 8 * c;
+            double lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { lo[u] = acc[t][u][0]; hi[u] = acc[t][u][1]; }
+            if (full) {
+                if (beta != 0.0) {
+                    double ol[4], oh[4];
+                    ld256_rw(po, ol);
+                    ld256_rw(po + 4, oh);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { lo[u] = fma(beta, ol[u], lo[u]); hi[u] = fma(beta, oh[u], hi[u]); }
+                }
+                st256(po, lo);
+                st256(po + 4, hi);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t r0 = R + 8 * c + u, r1 = r0 + 4;
+                    if (r0 < n) po[u] = beta != 0.0 ? fma(beta, po[u], lo[u]) : lo[u];
+                    if (r1 < n) po[u + 4] = beta != 0.0 ? fma(beta, po[u + 4], hi[u]) : hi[u];
+                }
+            }
+        }
+    }
+}
+
+static bool update_dmma_ok(const void* out, int64_t ldo, const void* x, int64_t ldx, int64_t k) {
+    return k <= UD_KMAX && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 31) == 0 &&
+           (ldo % 4 == 0) && (ldx % 4 == 0);
+}
+
+static int update_dmma(void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k, const void* q,
+                       int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, cudaStream_t st) {
+    int kp = (int)((k + 3) / 4 * 4);
+    while (kp % 16 != 4) kp += 4;                          // bank spread for the 64-bit fragment reads
+    const size_t smem = (size_t)UD_JB * kp * sizeof(double);
+    const int jblocks = (int)((m + UD_JB - 1) / UD_JB);
+    const int64_t nblocks = (n + 31) / 32;
+    // ~8 CTAs per SM in total, at least 4 row blocks per warp
+    int64_t want = ((int64_t)sm_count() * 8 + jblocks - 1) / jblocks;
+    int64_t maxc = (nblocks + UD_WARPS * 4 - 1) / (UD_WARPS * 4);
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    const int64_t bpc = (nblocks + want - 1) / want;
+    const unsigned gx = (unsigned)((nblocks + bpc - 1) / bpc);
+    const int nj = (int)(((m < UD_JB ? m : UD_JB) + 7) / 8);
+    static size_t configured[5] = {0, 0, 0, 0, 0};
+#define RL_UD_LAUNCH(NJ_)                                                                                        \
+    do {                                                                                                         \
+        if (smem > 48 * 1024 && smem > configured[NJ_]) {                                                        \
+            RL_CUDA(cudaFuncSetAttribute(update_dmma_kernel<NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)smem));                                                            \
+            configured[NJ_] = smem;                                                                              \
+        }                                                                                                        \
+        update_dmma_kernel<NJ_><<<dim3(gx, (unsigned)jblocks), UD_WARPS * 32, smem, st>>>(                       \
+            (double*)out, ldo, (int)m, (const double*)x, ldx, (int)k, (const double*)q, q_rs, q_cs, alpha, beta, \
+            n, kp, bpc);                                                                                         \
+    } while (0)
+    if (jblocks > 1 || nj == 4) RL_UD_LAUNCH(4);
+    else if (nj == 3) RL_UD_LAUNCH(3);
+    else if (nj == 2) RL_UD_LAUNCH(2);
+    else RL_UD_LAUNCH(1);
+#undef RL_UD_LAUNCH
+    return check_launch();
+}
+
 template <typename T>
 static int update_impl(void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k, const void* q,
                        int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, cudaStream_t st) {
@@ -157,6 +334,9 @@ using namespace rl;
 
 extern "C" {
 
+static int g_update_force_fma = 0;
+void rl_debug_set_update_fma(int on) { g_update_force_fma = on; }
+
 int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx, int64_t k, const void* q,
               int64_t q_rs, int64_t q_cs, double alpha, double beta, int64_t n, void* stream) {
     if (m < 0 || k < 0 || n < 0 || m > INT32_MAX || k > INT32_MAX) return RL_E_ARG;
@@ -175,6 +355,11 @@ int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64
     Span span(PK_UPDATE, st, (1.0 * k + (beta != 0.0 ? 2.0 : 1.0) * m) * n * (dtype == RL_F32 ? 4 : 8),
               2.0 * n * k * m);
     if (dtype == RL_F32) return update_impl<float>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
+    // measured on B200 (profiles/r1c_kernel_tuning.md): DMMA wins everywhere (m = 32: 84 % vs 47 % of HBM
+    // peak, m = 120: 28 vs 14 TFLOP/s) except the smallest beta = 0 blocks (m, k <= 16: 61 % vs 72 %)
+    const bool small_overwrite = beta == 0.0 && m <= 16 && k <= 16 && m > 8;
+    if (!g_update_force_fma && !small_overwrite && update_dmma_ok(out, ldo, x, ldx, k))
+        return update_dmma(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
     return update_impl<double>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);
 }
 

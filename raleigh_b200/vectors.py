@@ -32,6 +32,7 @@ def _np_type(t):
 class Vectors:
     """Block of vectors resident in HBM.  dense_cublas.py:17-632."""
 
+    HOST_RNG_MAX_ELEMENTS = 1 << 24   # above this fill_random() switches to the device RNG
     MIN_INC = 16      # capacity growth policy of the reference (dense_cublas.py:424-425)
     MAX_INC = 1024
 
@@ -215,10 +216,13 @@ class Vectors:
         m, n = self.nvec(), self._n
         if m < 1:
             return
-        if self._shard is not None:
-            # same seed on every rank (the host RNG streams are identical), rows keyed globally
+        if self._shard is not None or m * n > Vectors.HOST_RNG_MAX_ELEMENTS:
+            # Row-sharded or very large blocks (config 4: 16.8M x 120 would be 16 GB of host
+            # RNG + PCIe): counter-based device RNG, seeded from the host stream so that
+            # numpy.random.seed() still makes runs reproducible; same seed on every rank,
+            # rows keyed globally => independent of the partition.
             seed = int(numpy.random.randint(0, 2 ** 31 - 1))
-            self.fill_random_device(seed, row0=self._shard[1])
+            self.fill_random_device(seed, row0=self._shard[1] if self._shard is not None else 0)
             return
         data = numpy.random.rand(m, n).astype(self._dtype)
         data *= 2

@@ -115,6 +115,12 @@ def vec_suite(out, n, m, dtype, only):
         f = lambda: check(lib.rl_update(code, W._wptr(), W._ld, m, X._wptr(), X._ld, m, q.data_ptr(), m, 1, -1.0, 1.0, n, st()))
         ms, best = timeit(f)
         emit(out, 'update_beta1', shape, ms, best, 3 * blk, 2.0 * n * m * m)
+        if w == 8:
+            lib.rl_debug_set_update_fma(1)
+            f = lambda: check(lib.rl_update(code, W._wptr(), W._ld, m, X._wptr(), X._ld, m, q.data_ptr(), m, 1, 1.0, 0.0, n, st()))
+            ms, best = timeit(f)
+            lib.rl_debug_set_update_fma(0)
+            emit(out, 'update_beta0_fma', shape, ms, best, 2 * blk, 2.0 * n * m * m, 'FMA-pipe variant (A/B)')
     if 'blas1' in only:
         f = lambda: check(lib.rl_axpy(code, W._wptr(), W._ld, X._wptr(), X._ld, m, n, 0.5, st()))
         ms, best = timeit(f)
