@@ -385,6 +385,15 @@ def hbm_kernel_rates(peak_gbs):
     from raleigh_b200._lib import lib, check
     from raleigh_b200 import device as dev
     import scipy.sparse as sp
+    from raleigh_b200 import dist as rdist
+    saved, rdist._current = rdist._current, None     # single-GPU micro-measurement: no sharding, no collectives
+    try:
+        return _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp)
+    finally:
+        rdist._current = saved
+
+
+def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
     def timed(fn, reps=5):
@@ -453,6 +462,10 @@ def roofline_from(prof, peaks, steps):
 
 def main():
     args = parse()
+    wd = int(os.environ.get('RL_BENCH_WATCHDOG', '0'))
+    if wd > 0:      # debugging aid: dump every thread's stack if the run is still going after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
