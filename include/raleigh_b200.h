@@ -145,6 +145,7 @@ int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* 
  * two-warps-per-tile DMMA variant; rl_debug_set_update_fma forces the FMA-pipe update */
 void rl_debug_set_gram_simt(int on);
 void rl_debug_set_update_fma(int on);
+void rl_debug_set_spmm_warps(int warps);
 /* Vectors.multiply(q, out) dense_cublas.py:271-299 (gemm, beta=0) and
  * Vectors.add(other, s, q) dense_cublas.py:317-342 (gemm, beta=1):
  * Out[j,:] = beta*Out[j,:] + alpha * sum_{i<k} Q[i*q_rs + j*q_cs] * X[i,:], j < m.

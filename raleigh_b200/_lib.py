@@ -63,6 +63,7 @@ PROTOTYPES = {
     'rl_gram_acc64': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     'rl_debug_set_gram_simt': (None, [c_int]),
     'rl_debug_set_update_fma': (None, [c_int]),
+    'rl_debug_set_spmm_warps': (None, [c_int]),
     'rl_update': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_dbl, c_dbl,
                           c_i64, c_vp]),
     'rl_update_h': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_dbl, c_dbl,

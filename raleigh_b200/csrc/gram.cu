@@ -39,6 +39,7 @@ struct GramPlan {
 // bound by the number of load requests, not by occupancy -- one warp per 32x32
 // tile (NJ = 4, 248 registers, 8 warps/SM) with one 256-bit load per fragment
 // beats two warps side by side (JS = 2, 16 warps/SM) 64% to 49% of HBM peak.
+static int g_gram_prefetch = 0;  // L2 prefetch distance in steps (0 = off; measured: any distance 1..8 costs 35 %)
 static int g_gram_variant = 0;   // debug: 1 = two warps side by side per 32-wide tile (NJ = 2, JS = 2)
 
 static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, i
 template <int NI, int NJ, int JS, bool SAME>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double* __restrict__ O, int64_t ldo,
-                 int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part) {
+                 int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part, int g_pf) {
     constexpr int RW = GRAM_WARPS / JS;              // warps interleaving row steps
     __shared__ double red[RW][JS * NI * NJ * 64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,6 +121,17 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
         // full 16-row steps, one 256-bit load per fragment
         for (; r + 16 <= c_end; r += 16 * RW) {
             double fa[NI][4], fb[NJ][4];
+            if (g_pf > 0 && r + (int64_t)g_pf * 16 * RW + 16 <= c_end) {
+                // pull the fragments of a later step into L2 while this one computes
+#pragma unroll
+                for (int t = 0; t < NI; ++t)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(po[t] + r + (int64_t)g_pf * 16 * RW + 4 * c));
+                if (!SAME) {
+#pragma unroll
+                    for (int t = 0; t < NJ; ++t)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[t] + r + (int64_t)g_pf * 16 * RW + 4 * c));
+                }
+            }
 #pragma unroll
             for (int t = 0; t < NI; ++t) load4<true>(po[t], r + 4 * c, n, ai[t], fa[t]);
             if (SAME) {
@@ -272,7 +284,7 @@ static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
     const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1 && p.ni == p.nj && p.js == 1;
 #define RL_GRAM_LAUNCH(NJ_, JS_, SAME_) \
-    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part)
+    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch)
     if (same) {
         RL_GRAM_LAUNCH(NI, 1, true);
     } else if (p.nj == 4) {
@@ -317,7 +329,7 @@ extern "C" {
 // gram_mode: 0 = dtype default (fp64 -> DMMA, fp32 -> SIMT fp32 accumulate),
 //            1 = force SIMT, 2 = fp32 data with fp64 accumulation and fp64 output
 static int g_gram_force_simt = 0;
-void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on & 1; g_gram_variant = (on >> 1) & 1; }
+void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on & 1; g_gram_variant = (on >> 1) & 1; g_gram_prefetch = (on >> 8) & 255; }
 
 static size_t gram_ws_bytes_impl(int dtype, int64_t m, int64_t k, int64_t n, int acc64) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;

@@ -16,7 +16,10 @@
 
 namespace rl {
 
-constexpr int SPMM_WARPS = 4;
+// Warps per CTA.  Consecutive rows share gathered lines (stencil neighbours at +-1, +-N):
+// the more consecutive rows a CTA covers, the more of those gathers hit L1 instead of L2.
+// Measured on B200 (profiles/r1c_kernel_tuning.md).
+static int g_spmm_warps = 4;     // 16-warp CTAs measured slower (2.2 vs 3.2 TB/s on 128^3 and 256^3 Laplacians): their staging buffers shrink L1
 
 // Column c of the operator: owned columns come from the local block X (vector-major),
 // halo columns (c >= ncols_local, row-sharded operator) from the exchanged halo buffer H,
@@ -28,7 +31,7 @@ __device__ __forceinline__ T xval(const T* __restrict__ X, int64_t ldx, const T*
                                              : __ldg(H + (int64_t)(c - ncols_local) * m + v);
 }
 
-template <typename T, int VG>
+template <typename T, int VG, int SPMM_WARPS>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
@@ -114,22 +117,39 @@ template <typename T>
 static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
                      const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
                      cudaStream_t st) {
-    // shared-memory capacity per warp: twice the average entries of 32 rows,
-    // rounded to a power of two in [256, 4096]
+    // shared-memory capacity per warp: the average entries of 32 rows + 25 %, in [256, 4096];
+    // warps whose segment is longer read the matrix from global memory instead
     int64_t avg = nrows > 0 ? (nnz * 32 + nrows - 1) / nrows : 0;
-    int cap = 256;
-    while (cap < 2 * avg && cap < 4096) cap *= 2;
-    size_t smem = (size_t)SPMM_WARPS * cap * (sizeof(T) + 4);
+    int64_t want = (avg * 5 / 4 + 63) / 64 * 64;            // 25 % head room over the average 32-row segment
+    int cap = (int)(want < 256 ? 256 : want > 4096 ? 4096 : want);
     constexpr int VG = 8;
-    auto kern = spmm_kernel<T, VG>;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // big CTAs only when the staged entries of all their warps leave most of L1 free
+    const bool wide = g_spmm_warps >= 16 && (size_t)16 * cap * (sizeof(T) + 4) <= 96 * 1024;
+    if (wide) {
+        constexpr int W = 16;
+        size_t smem = (size_t)W * cap * (sizeof(T) + 4);
+        auto kern = spmm_kernel<T, VG, W>;
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
+        kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
+                                                     (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
+    } else {
+        constexpr int W = 4;
+        size_t smem = (size_t)W * cap * (sizeof(T) + 4);
+        auto kern = spmm_kernel<T, VG, W>;
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
+        kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
+                                                     (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
     }
-    int64_t blocks = (nrows + SPMM_WARPS * 32 - 1) / (SPMM_WARPS * 32);
-    kern<<<(unsigned)blocks, SPMM_WARPS * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
-                                                          (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
     return check_launch();
 }
 
@@ -229,6 +249,8 @@ pack_rows_kernel(const T* __restrict__ X, int64_t ldx, int m, const int64_t* __r
 using namespace rl;
 
 extern "C" {
+
+void rl_debug_set_spmm_warps(int warps) { g_spmm_warps = warps; }
 
 int rl_pack_rows(int dtype, const void* x, int64_t ldx, int64_t m, const int64_t* idx, int64_t count, void* out,
                  void* stream) {
