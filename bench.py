@@ -214,7 +214,9 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 's', 'n_gpus': args.gpus,
         'steps': args.steps, 'steps_executed': len(times), 'warmup': args.warmup, 'ms_per_step': val * 1e3,
         'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': val / 27.0, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(args, 1),
+        'data': 'synthetic', 'config': dict(workload_config(args, 1), parallelism='host CPU, %d cores' % os.cpu_count(),
+                                                 solver='reference core solver + lra/partial_svd on the reference\'s own '
+                                                        'dense_numpy algebra (NumPy/OpenBLAS; MKL not installable)'),
         'cpu_baseline': {'value': val, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference', 'sample': desc},
         'e2e': {'value': val, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'components': int(ncomp),
@@ -260,7 +262,20 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     ctx = None
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL prints its version banner on stdout when NCCL_DEBUG asks for it; keep stdout
+        # for the single JSON line by pointing fd 1 at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            warm = torch.zeros(1, device='cuda')
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         from raleigh_b200 import dist as rdist
         ctx = rdist.enable()
 
@@ -339,6 +354,13 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     roof = roofline_from(prof, peaks, args.steps)
+    try:        # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'dense_apply_tc_ncu.json')))
+        if roof and roof['kernel'] == 'dense_apply_tc' and (args.rows, args.cols) == (M_ROWS, N_COLS):
+            roof['traffic'] = cap['dram_bytes_per_launch']
+            roof['traffic_source'] = cap['source']
+    except Exception:
+        pass
     val_s = ms_val / 1e3 / args.steps
     e2e_s = ms_e2e / 1e3 / args.steps
     line = {
@@ -358,6 +380,7 @@ def run_b200(args, rank, world, local_rank):
         line['hbm_kernels'] = hbm_kernel_rates(peaks.get('hbm_gbs') or 6650.0)
     except Exception as exc:
         line['hbm_kernels'] = {'error': repr(exc)}
+    line['impl'] = 'raleigh_b200'
     if ctx is not None:
         line['collectives'] = {'allreduce_calls': ctx.allreduce_calls, 'allreduce_MB': round(ctx.allreduce_bytes / 1e6, 1)}
     host_limit.restore_original_limits()

@@ -68,6 +68,12 @@ class _NumpyProxy:
         return self._np.eye(int(n), *args, **kwargs)
 
 
+def _int_min(*args, **kwargs):
+    import builtins
+    r = builtins.min(*args, **kwargs)
+    return int(r) if isinstance(r, float) else r
+
+
 def shim_scipy():
     """Version shims the reference needs on ANY backend with current SciPy/NumPy;
     they touch no algebra."""
@@ -80,6 +86,10 @@ def shim_scipy():
         import raleigh.interfaces.partial_svd as psvd
         if not isinstance(psvd.numpy, _NumpyProxy):
             psvd.numpy = _NumpyProxy(numpy)
+        # `nv = min(32, nsv/2)` (partial_svd.py:201) is Python-2 integer division: under
+        # Python 3 it yields a float that then breaks `select()` / slicing on the reference's
+        # own NumPy backend.  A module-level `min` restores the integer result.
+        psvd.min = _int_min
     except ImportError:
         pass
 
