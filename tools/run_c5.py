@@ -1,0 +1,58 @@
+"""BASELINE config 5 (reduced): incremental chunked PCA, pca(A, tol=..., batch_size=...) on the
+GPU backend (lra.icompute / lra.update run verbatim: chunk-as-vectors dots, mean update,
+orthogonalize against the components, deflated solve, svd-based re-orthogonalisation).
+
+    python tools/run_c5.py [--rows 262144] [--cols 4096] [--chunk 65536] [--tol 0.05] [--cpu]
+"""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from threadpoolctl import threadpool_limits
+import raleigh_b200 as rb
+from raleigh_b200 import profile
+rb.install()
+from raleigh.interfaces.pca import pca
+from raleigh.core.solver import Options
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--rows', type=int, default=262144)
+ap.add_argument('--cols', type=int, default=4096)
+ap.add_argument('--chunk', type=int, default=65536)
+ap.add_argument('--rank', type=int, default=256)
+ap.add_argument('--tol', type=float, default=0.05)
+ap.add_argument('--cpu', action='store_true')
+args = ap.parse_args()
+
+g = torch.Generator(device='cuda'); g.manual_seed(1)
+r = args.rank
+sigma = torch.arange(1, r + 1, device='cuda', dtype=torch.float32) ** (-0.75)
+v, _ = torch.linalg.qr(torch.randn(args.cols, r, generator=g, device='cuda'))
+u = torch.randn(args.rows, r, generator=g, device='cuda') / args.rows ** 0.5
+a = (u * sigma[None, :]) @ v.T
+a += 1e-3 * sigma[-1] * torch.randn(args.rows, args.cols, generator=g, device='cuda') / args.cols ** 0.5
+A = a.cpu().numpy()
+with threadpool_limits(limits=1):
+    np.random.seed(1)
+    profile.reset(); profile.enable(True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    mean, trans, comps = pca(A, tol=args.tol, batch_size=args.chunk, arch='gpu!', opt=Options())
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    profile.enable(False)
+prof = profile.report()
+t = torch.as_tensor(trans, device='cuda'); c = torch.as_tensor(comps, device='cuda')
+ds = a - torch.as_tensor(mean, device='cuda').reshape(1, -1)
+ef = (torch.linalg.norm(t @ c - ds) / torch.linalg.norm(ds)).item()
+line = {'config': 'C5 (reduced): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (args.rows, args.cols, args.chunk, args.tol),
+        'gpu_s': round(dt, 3), 'components': int(comps.shape[0]), 'pca_error_frobenius': ef,
+        'device_ms': round(sum(v_['ms'] for v_ in prof.values()), 1),
+        'kernels': {k: {'count': v_['count'], 'ms': round(v_['ms'], 1)} for k, v_ in prof.items()}}
+if args.cpu:
+    from bench import load_reference_cpu
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    mean2, trans2, comps2 = pca(A, tol=args.tol, batch_size=args.chunk, arch='cpu', opt=Options())
+    line['cpu_s'] = round(time.perf_counter() - t0, 2)
+    line['cpu_components'] = int(comps2.shape[0])
+print(json.dumps(line), flush=True)
