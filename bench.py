@@ -171,9 +171,18 @@ def cpu_pca_seconds(a_host, npc, budget_s=60.0):
         frac = max(0.1, (budget_s / est) ** 0.5)
     r, k = int(rows * frac), max(8, int(npc * frac))
     sample = a_host if frac == 1.0 else np.ascontiguousarray(a_host[:r])
+    from raleigh.interfaces.lra import LowerRankApproximation
+    from raleigh.algebra.dense_matrix import AMatrix
     t0 = time.perf_counter()
-    mean, trans, comps = pca(sample, npc=k, arch='cpu', opt=Options())
+    # exactly what pca(sample, npc=k, arch='cpu') does (pca.py:142-153), spelled out so that
+    # the solver's iteration count can be reported next to the GPU run's
+    lra = LowerRankApproximation()
+    lra.ortho = 1e-3 if sample.shape[0] < sample.shape[1] else 0
+    lra.compute(AMatrix(sample, arch='cpu'), opt=Options(), rank=k, tol=0, norm='f', max_rank=-1, svtol=1e-3,
+                shift=True, verb=0)
+    trans, comps, mean = lra.left(), lra.right(), lra.mean()
     t = time.perf_counter() - t0
+    cpu_pca_seconds.last_iterations = int(lra.iterations)
     if frac == 1.0:
         desc = 'full C2 workload: pca(%dx%d fp32, npc=%d), reference dense_numpy on NumPy/OpenBLAS (not MKL)' % (
             rows, cols, npc)
@@ -219,7 +228,7 @@ def run_reference(args, rank, world):
                                                         'dense_numpy algebra (NumPy/OpenBLAS; MKL not installable)'),
         'cpu_baseline': {'value': val, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference', 'sample': desc},
         'e2e': {'value': val, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'components': int(ncomp),
+        'components': int(ncomp), 'solver_iterations': getattr(cpu_pca_seconds, 'last_iterations', None),
     }
     print(json.dumps(line))
 
@@ -390,7 +399,8 @@ def run_b200(args, rank, world, local_rank):
             np.random.seed(1)
             t, desc, _ = cpu_pca_seconds(a_host, args.npc, budget_s=45.0)
             line['cpu_baseline'] = {'value': t, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference',
-                                    'sample': desc}
+                                    'sample': desc,
+                                    'solver_iterations': getattr(cpu_pca_seconds, 'last_iterations', None)}
         except Exception as exc:  # the baseline must never cost us the measured line
             line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference',
                                     'sample': 'failed: %r' % (exc,)}

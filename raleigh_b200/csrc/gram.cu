@@ -27,6 +27,7 @@ constexpr int GRAM_WARPS = 4;
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;
 
 struct GramPlan {
+    int warps;           // warps per CTA of the DMMA kernel
     int ni, nj, js;      // 8-wide fragments per WARP tile along k (other) and m (self); warps side by side along m
     int tiles_i, tiles_j;
     int chunks;          // row chunks (CTAs along the reduction)
@@ -40,6 +41,8 @@ struct GramPlan {
 // tile (NJ = 4, 248 registers, 8 warps/SM) with one 256-bit load per fragment
 // beats two warps side by side (JS = 2, 16 warps/SM) 64% to 49% of HBM peak.
 static int g_gram_prefetch = 0;  // L2 prefetch distance in steps (0 = off; measured: any distance 1..8 costs 35 %)
+static int g_gram_warps8 = 0;
+static int g_gram_minb = 0;      // debug: register cap of the 32x32 variant via min CTAs/SM (3 -> 168 regs, 4 -> 128)
 static int g_gram_variant = 0;   // debug: 1 = two warps side by side per 32-wide tile (NJ = 2, JS = 2)
 
 static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
@@ -47,10 +50,13 @@ static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
     auto frag = [](int64_t v) { return v <= 8 ? 1 : v <= 16 ? 2 : 4; };
     p.ni = frag(k);
     if (m > 16 && g_gram_variant == 1) { p.nj = 2; p.js = 2; } else { p.nj = frag(m); p.js = 1; }
+    // 8 interleaved warps on the big tile: the CTA then reads 1 KB (instead of 512 B) of every
+    // vector per step -- DRAM-page locality; same 8 warps per SM either way (248 registers)
+    p.warps = (p.ni == 4 && p.nj == 4 && g_gram_warps8) ? 8 : GRAM_WARPS;
     p.tiles_i = (int)((k + 8 * p.ni - 1) / (8 * p.ni));
     p.tiles_j = (int)((m + 8 * p.nj * p.js - 1) / (8 * p.nj * p.js));
     int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
-    const int64_t step = 16 * (GRAM_WARPS / p.js);          // rows a CTA consumes per step
+    const int64_t step = 16 * (p.warps / p.js);             // rows a CTA consumes per step
     // enough CTAs for ~6 per SM, but at least 4 steps per CTA
     int64_t want = ((int64_t)sm_count() * 6 + tiles - 1) / tiles;
     int64_t maxc = (n + 4 * step - 1) / (4 * step);
@@ -87,12 +93,14 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, i
     }
 }
 
-template <int NI, int NJ, int JS, bool SAME>
-__global__ void __launch_bounds__(GRAM_THREADS)
+template <int NI, int NJ, int JS, bool SAME, int MINB = 1, int DW = GRAM_WARPS>
+__global__ void __launch_bounds__(DW * 32, MINB)
 gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double* __restrict__ O, int64_t ldo,
                  int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part, int g_pf) {
-    constexpr int RW = GRAM_WARPS / JS;              // warps interleaving row steps
-    __shared__ double red[RW][JS * NI * NJ * 64];
+    constexpr int RW = DW / JS;                      // warps interleaving row steps
+    constexpr int TILE = JS * NI * NJ * 64;
+    extern __shared__ double red_raw[];
+    double (*red)[TILE] = reinterpret_cast<double (*)[TILE]>(red_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int jw = warp % JS, rw = warp / JS;
     const int g = lane >> 2, c = lane & 3;
@@ -176,7 +184,7 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
     __syncthreads();
     double* out = part + (int64_t)chunk * k * m;
     const int jbase = blockIdx.y * (8 * NJ * JS);
-    for (int e = threadIdx.x; e < JS * NI * NJ * 64; e += GRAM_THREADS) {
+    for (int e = threadIdx.x; e < TILE; e += DW * 32) {
         double v = red[0][e];
 #pragma unroll
         for (int w = 1; w < RW; ++w) v += red[w][e];
@@ -284,9 +292,19 @@ static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
     const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1 && p.ni == p.nj && p.js == 1;
 #define RL_GRAM_LAUNCH(NJ_, JS_, SAME_) \
-    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, 0, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch)
+    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, (GRAM_WARPS / JS_) * JS_ * NI * NJ_ * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch)
     if (same) {
         RL_GRAM_LAUNCH(NI, 1, true);
+    } else if (p.nj == 4 && NI == 4 && p.warps == 8) {
+        constexpr size_t smem8 = 8 * NI * 4 * 64 * sizeof(double);          // 64 KB of partial tiles
+        static bool configured = false;
+        if (!configured) {
+            RL_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<NI, 4, 1, false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            configured = true;
+        }
+        gram_dmma_kernel<NI, 4, 1, false, 1, 8><<<grid, 256, smem8, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch);
+    } else if (p.nj == 4 && NI == 4 && g_gram_minb == 3) {
+        gram_dmma_kernel<NI, 4, 1, false, 3><<<grid, GRAM_THREADS, 4 * NI * 4 * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch);
     } else if (p.nj == 4) {
         RL_GRAM_LAUNCH(4, 1, false);
     } else if (p.js == 2) {
@@ -329,7 +347,7 @@ extern "C" {
 // gram_mode: 0 = dtype default (fp64 -> DMMA, fp32 -> SIMT fp32 accumulate),
 //            1 = force SIMT, 2 = fp32 data with fp64 accumulation and fp64 output
 static int g_gram_force_simt = 0;
-void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on & 1; g_gram_variant = (on >> 1) & 1; g_gram_prefetch = (on >> 8) & 255; }
+void rl_debug_set_gram_simt(int on) { g_gram_force_simt = on & 1; g_gram_variant = (on >> 1) & 1; g_gram_prefetch = (on >> 8) & 255; g_gram_minb = (on >> 16) & 7; g_gram_warps8 = (on >> 20) & 1; }
 
 static size_t gram_ws_bytes_impl(int dtype, int64_t m, int64_t k, int64_t n, int acc64) {
     if (m <= 0 || k <= 0 || n <= 0) return 0;
