@@ -146,6 +146,10 @@ int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* 
 void rl_debug_set_gram_simt(int on);
 void rl_debug_set_update_fma(int on);
 void rl_debug_set_spmm_warps(int warps);
+/* generic A/B knob (0 = library default): 0 = TMA-fed fp64 Gram (1 on / -1 off, 2 = shallow ring),
+ * 1 = SpMM kernel (1 = staged CSR, 2 = SELL-32, 3 = footprint-staged), 2/3 = its vector group / rows per CTA */
+void rl_debug_set_knob(int knob, int value);
+int rl_debug_get_knob(int knob);
 /* Vectors.multiply(q, out) dense_cublas.py:271-299 (gemm, beta=0) and
  * Vectors.add(other, s, q) dense_cublas.py:317-342 (gemm, beta=1):
  * Out[j,:] = beta*Out[j,:] + alpha * sum_{i<k} Q[i*q_rs + j*q_cs] * X[i,:], j < m.
@@ -194,6 +198,22 @@ int rl_dense_apply_tc(const void* a, const void* a_lo, int64_t lda, int64_t M, i
 int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr,
                 const int32_t* indices, const void* values, const void* x, int64_t ldx,
                 void* y, int64_t ldy, int64_t m, void* stream);
+
+/* Extended form: `run_order` (device, ceil(nrows/32) entries, or NULL = identity) maps CTA slots to
+ * 32-row runs -- see rl_spmm_cluster_runs; `warps` = runs per CTA (4, 8 or 16; 0 = default);
+ * ncols_local/halo as in rl_csr_spmm_halo (0/NULL when the operator is not sharded). */
+int rl_csr_spmm_ex(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                   const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                   int64_t ncols_local, const void* halo, const int32_t* run_order, int warps,
+                   void* stream);
+/* HOST-side set-up (no device work; all pointers are host arrays): a permutation of the 32-row
+ * runs of the CSR matrix such that every `group` consecutive entries (the runs one CTA of
+ * rl_csr_spmm_ex processes together) share as much of their column footprint as possible, so the
+ * X lines gathered for one warp are L1 hits for the others.  footprint_ratio_out (optional):
+ * distinct 32-column segments gathered per CTA, summed, divided by the number of runs (1 = every
+ * X line enters an SM once). */
+int rl_spmm_cluster_runs(int64_t nrows, const int64_t* indptr_h, const int32_t* indices_h, int group,
+                         int32_t* order_out_h, double* footprint_ratio_out);
 
 /* Same product from the SELL-32 layout (sliced ELLPACK, 32-row slices): entry j
  * of row 32*s + l is stored at slice_ptr[s] + 32*j + l; padding entries have

@@ -64,6 +64,8 @@ PROTOTYPES = {
     'rl_debug_set_gram_simt': (None, [c_int]),
     'rl_debug_set_update_fma': (None, [c_int]),
     'rl_debug_set_spmm_warps': (None, [c_int]),
+    'rl_debug_set_knob': (None, [c_int, c_int]),
+    'rl_debug_get_knob': (c_int, [c_int]),
     'rl_update': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_dbl, c_dbl,
                           c_i64, c_vp]),
     'rl_update_h': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_dbl, c_dbl,
@@ -76,6 +78,9 @@ PROTOTYPES = {
     'rl_dense_apply_tc': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_int,
                                   c_dbl, c_dbl, c_vp, c_sz, c_vp]),
     'rl_csr_spmm': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    'rl_csr_spmm_ex': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
+                               c_vp, c_int, c_vp]),
+    'rl_spmm_cluster_runs': (c_int, [c_i64, c_vp, c_vp, c_int, c_vp, ctypes.POINTER(c_dbl)]),
     'rl_sell_spmm': (c_int, [c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     'rl_pack_rows': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     'rl_csr_spmm_halo': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,

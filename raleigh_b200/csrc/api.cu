@@ -10,6 +10,7 @@ namespace rl {
 
 int64_t g_launches = 0;
 int g_profile_on = 0;
+int g_knob[KNOB_COUNT] = {0};
 
 namespace {
 struct ProfRec { int kind; cudaEvent_t a, b; double bytes, flops; };
@@ -184,6 +185,9 @@ int rl_profile_get(int kind, int64_t* count, double* ms, double* bytes, double* 
     if (flops) *flops = s.flops;
     return 0;
 }
+
+void rl_debug_set_knob(int knob, int value) { if (knob >= 0 && knob < KNOB_COUNT) g_knob[knob] = value; }
+int rl_debug_get_knob(int knob) { return (knob >= 0 && knob < KNOB_COUNT) ? g_knob[knob] : 0; }
 
 int rl_sync_device(void) { return (int)cudaDeviceSynchronize(); }
 int rl_sync_stream(void* stream) { return (int)cudaStreamSynchronize(as_stream(stream)); }

@@ -10,6 +10,9 @@
 namespace rl {
 
 extern int64_t g_launches;          // kernels launched by this library (api.cu)
+// A/B knobs set through rl_debug_set_knob (api.cu); 0 = library default everywhere
+enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_MODE = 1, KNOB_SPMM_VG = 2, KNOB_SPMM_ROWS = 3, KNOB_COUNT = 16 };
+extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 
 inline int check_launch() {
@@ -47,6 +50,22 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double ldg_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 

@@ -31,6 +31,7 @@
 // M, N, K and fewer than 128 vectors need no special code in the main loop.
 #include <cuda.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace rl {
 
@@ -51,34 +52,7 @@ struct TcParams {
     float alpha, beta;
 };
 
-// ---- PTX wrappers ------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
+// mbarrier / TMA wrappers: tma.cuh
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -322,36 +296,6 @@ split_tf32_kernel(const float* __restrict__ src, int64_t ld_src, float* __restri
 }
 
 // ---- host side ------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-static int make_map(CUtensorMap* map, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_inner,
-                    int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return RL_E_ARG;
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : RL_E_ARG;
-}
-
 struct TcPlan { int tiles, vblocks, splits, kblocks, kb_per_split; int64_t ld_ws; size_t ws_bytes, xlo_bytes; int64_t ld_xlo; };
 
 static TcPlan tc_plan(int64_t M, int64_t N, int64_t k, int transp) {
@@ -381,7 +325,7 @@ static TcPlan tc_plan(int64_t M, int64_t N, int64_t k, int transp) {
 }
 
 bool gemm_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx) {
-    return encode_fn() != nullptr && host_aligned16(a) && host_aligned16(x) && (lda % 4 == 0) && (ldx % 4 == 0);
+    return tma_encode_fn() != nullptr && host_aligned16(a) && host_aligned16(x) && (lda % 4 == 0) && (ldx % 4 == 0);
 }
 
 int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_t N, const float* x, int64_t ldx,
@@ -398,14 +342,14 @@ int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_
         if (rc) return rc;
     }
     CUtensorMap mxh, mxl, mah, mal;
-    int rc = make_map(&mxh, x, kred, k, ldx, TC_BK, TC_BM);
-    if (!rc) rc = make_map(&mxl, x_lo, kred, k, pl.ld_xlo, TC_BK, TC_BM);
+    int rc = make_map(&mxh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, kred, k, ldx, TC_BK, TC_BM);
+    if (!rc) rc = make_map(&mxl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x_lo, kred, k, pl.ld_xlo, TC_BK, TC_BM);
     if (!transp) {
-        if (!rc) rc = make_map(&mah, a_hi, N, M, lda, TC_BK, TC_BN);
-        if (!rc) rc = make_map(&mal, a_lo, N, M, lda, TC_BK, TC_BN);
+        if (!rc) rc = make_map(&mah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_hi, N, M, lda, TC_BK, TC_BN);
+        if (!rc) rc = make_map(&mal, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_lo, N, M, lda, TC_BK, TC_BN);
     } else {
-        if (!rc) rc = make_map(&mah, a_hi, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-        if (!rc) rc = make_map(&mal, a_lo, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!rc) rc = make_map(&mah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_hi, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!rc) rc = make_map(&mal, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_lo, N, M, lda, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     }
     if (rc) return rc;
     TcParams p;

@@ -24,6 +24,9 @@
 namespace rl {
 
 constexpr int GRAM_WARPS = 4;
+#ifndef RL_GRAM_TMA_DEFAULT
+#define RL_GRAM_TMA_DEFAULT 0   // until measured on B200: register-fragment kernel stays the default
+#endif
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;
 
 struct GramPlan {
@@ -44,6 +47,12 @@ static int g_gram_prefetch = 0;  // L2 prefetch distance in steps (0 = off; meas
 static int g_gram_warps8 = 0;
 static int g_gram_minb = 0;      // debug: register cap of the 32x32 variant via min CTAs/SM (3 -> 168 regs, 4 -> 128)
 static int g_gram_variant = 0;   // debug: 1 = two warps side by side per 32-wide tile (NJ = 2, JS = 2)
+
+// gram_tma.cu
+bool gram_tma_ok(const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k, int64_t n);
+size_t gram_tma_ws_bytes(int64_t m, int64_t k, int64_t n);
+int gram_tma(const double* S, int64_t lds, int64_t m, const double* O, int64_t ldo, int64_t k, int64_t n, double* part,
+             int* chunks_out, int mode, cudaStream_t st);
 
 static GramPlan gram_plan(int64_t m, int64_t k, int64_t n) {
     GramPlan p;
@@ -353,7 +362,8 @@ static size_t gram_ws_bytes_impl(int dtype, int64_t m, int64_t k, int64_t n, int
     if (m <= 0 || k <= 0 || n <= 0) return 0;
     if (dtype == RL_F64 && !g_gram_force_simt) {
         GramPlan p = gram_plan(m, k, n);
-        return (size_t)p.chunks * k * m * sizeof(double);
+        size_t a = (size_t)p.chunks * k * m * sizeof(double), b = n >= 8192 ? gram_tma_ws_bytes(m, k, n) : 0;
+        return a > b ? a : b;
     }
     GramPlan p = gram_plan_simt(m, k, n, dtype == RL_F32 ? 4 : 2);
     return (size_t)p.chunks * k * m * ((dtype == RL_F64 || acc64) ? 8 : 4);
@@ -378,6 +388,15 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
     int rc;
     int chunks;
     if (dtype == RL_F64 && !g_gram_force_simt) {
+        // TMA-fed ring variant (gram_tma.cu): KNOB_GRAM_TMA 0 = default policy, -1 = off, 1/2 = forced mode
+        const int tma_knob = g_knob[KNOB_GRAM_TMA];
+        const int tma_mode = tma_knob > 0 ? tma_knob : (tma_knob == 0 ? RL_GRAM_TMA_DEFAULT : 0);
+        if (tma_mode > 0 && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
+            rc = gram_tma((const double*)s, lds, m, (const double*)o, ldo, k, n, (double*)ws, &chunks, tma_mode, st);
+            if (rc) return rc;
+            gram_reduce_kernel<double, double><<<(unsigned)((km * 8 + 255) / 256), 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+            return check_launch();
+        }
         GramPlan p = gram_plan(m, k, n);
         int fast = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 31) == 0 &&
                    (lds % 4 == 0) && (ldo % 4 == 0);

@@ -1,0 +1,230 @@
+// TMA-fed variant of the fp64 Gram kernel (gram.cu).
+//
+// gram_dmma_kernel is bound by the number of load REQUESTS it can keep in flight
+// (profiles/r1c_kernel_tuning.md: going from 128-bit to 256-bit fragment loads took it
+// from 41 % to 64 % of HBM peak, more warps did nothing; its 248 registers leave no room
+// for a second set of fragments in flight).  Here a producer lane moves 16-row x
+// (8*NI | 8*NJ)-vector boxes with cp.async.bulk.tensor into a shared-memory ring, so
+// memory latency is hidden by the ring instead of by registers, and four consumer warps
+// read their DMMA fragments with conflict-free 128-bit shared loads (128B-swizzled rows:
+// lane (g, c) needs bytes [32c, 32c+32) of vector row g, 16-byte chunks 2c^g and (2c+1)^g).
+// Out-of-range rows / vectors are zero-filled by TMA, so there is no tail code.
+//
+// Stage layout: 4 warps x KSUB sub-steps x { O box (NI KB) | S box (NJ KB) }, where a box is
+// 16 rows of 8*NI (8*NJ) vectors; KSUB is chosen so that a warp consumes ~8 KB per stage.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace rl {
+
+constexpr int GT_THREADS = 160;                // 4 consumer warps + 1 producer warp
+
+__host__ __device__ constexpr int gt_ksub(int ni, int nj) { return (8 / (ni + nj)) > 0 ? 8 / (ni + nj) : 1; }
+__host__ __device__ constexpr int gt_stage_bytes(int ni, int nj) { return 4 * gt_ksub(ni, nj) * (ni + nj) * 1024; }
+__host__ __device__ constexpr int gt_smem(int ni, int nj, int stages) { return stages * gt_stage_bytes(ni, nj) + 1024 + 256; }
+
+__device__ __forceinline__ void gt_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NI, int NJ, bool SAME, int STAGES, int MINB>
+__global__ void __launch_bounds__(GT_THREADS, MINB)
+gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_s, int m, int k,
+                int64_t n, int64_t rows_per_cta, double* __restrict__ part) {
+    constexpr int KSUB = gt_ksub(NI, NJ);
+    constexpr int OBOX = NI * 1024, SBOX = NJ * 1024, SUB = OBOX + SBOX;
+    constexpr int STAGE = gt_stage_bytes(NI, NJ);
+    constexpr int ROWS = 64 * KSUB;                      // rows per stage
+    extern __shared__ uint8_t smem_raw[];
+    // pointer arithmetic on the __shared__ symbol keeps the address space (LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ);
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_end = r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n;
+    const int nstages = (int)((r_end - r_begin + ROWS - 1) / ROWS);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < nstages; ++it) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * STAGE;
+                mbar_expect_tx(&full[stage], 4 * KSUB * (SAME ? OBOX : SUB));
+                const int64_t r0 = r_begin + (int64_t)it * ROWS;
+#pragma unroll
+                for (int q = 0; q < 4 * KSUB; ++q) {
+                    // sub-step q = warp * KSUB + u covers rows r0 + 16 q
+                    tma_load_2d(st + q * SUB, &tm_o, &full[stage], (int)(r0 + 16 * q), i0);
+                    if (!SAME) tma_load_2d(st + q * SUB + OBOX, &tm_s, &full[stage], (int)(r0 + 16 * q), j0);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp w owns sub-steps w*KSUB .. w*KSUB+KSUB-1 of every stage ----------
+    const int g = lane >> 2, c = lane & 3;
+    const uint32_t ch0 = (uint32_t)((2 * c) ^ g) * 16, ch1 = (uint32_t)((2 * c + 1) ^ g) * 16;
+    double acc[NI][NJ][2];
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < nstages; ++it) {
+        mbar_wait(&full[stage], phase);
+#pragma unroll
+        for (int u = 0; u < KSUB; ++u) {
+            const uint8_t* bo = smem + stage * STAGE + (warp * KSUB + u) * SUB;
+            const uint8_t* bs = bo + OBOX;
+            double fa[NI][4], fb[NJ][4];
+#pragma unroll
+            for (int t = 0; t < NI; ++t) {
+                const uint8_t* row = bo + (8 * t + g) * 128;
+                const double2 x0 = *reinterpret_cast<const double2*>(row + ch0);
+                const double2 x1 = *reinterpret_cast<const double2*>(row + ch1);
+                fa[t][0] = x0.x; fa[t][1] = x0.y; fa[t][2] = x1.x; fa[t][3] = x1.y;
+            }
+            if (SAME) {
+#pragma unroll
+                for (int t = 0; t < NJ; ++t)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) fb[t][e] = fa[t < NI ? t : 0][e];
+            } else {
+#pragma unroll
+                for (int t = 0; t < NJ; ++t) {
+                    const uint8_t* row = bs + (8 * t + g) * 128;
+                    const double2 x0 = *reinterpret_cast<const double2*>(row + ch0);
+                    const double2 x1 = *reinterpret_cast<const double2*>(row + ch1);
+                    fb[t][0] = x0.x; fb[t][1] = x0.y; fb[t][2] = x1.x; fb[t][3] = x1.y;
+                }
+            }
+            if (u == KSUB - 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);   // fragments are in registers: release the slot
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int a = 0; a < NI; ++a)
+#pragma unroll
+                    for (int b = 0; b < NJ; ++b) gt_dmma(acc[a][b][0], acc[a][b][1], fa[a][s], fb[b][s]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // cross-warp reduction through the (now idle) ring: every TMA write has been consumed
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    constexpr int TILE = NI * NJ * 64;
+    double* red = reinterpret_cast<double*>(smem);            // 4 warps x TILE doubles <= 32 KB
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ; ++b) {
+            red[warp * TILE + (a * NJ + b) * 64 + g * 8 + 2 * c] = acc[a][b][0];
+            red[warp * TILE + (a * NJ + b) * 64 + g * 8 + 2 * c + 1] = acc[a][b][1];
+        }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    double* out = part + (int64_t)blockIdx.x * k * m;
+    for (int e = threadIdx.x; e < TILE; e += 128) {
+        const double v = (red[e] + red[TILE + e]) + (red[2 * TILE + e] + red[3 * TILE + e]);
+        const int blk = e >> 6, a = blk / NJ, b = blk % NJ;
+        const int i = i0 + 8 * a + ((e & 63) >> 3), j = j0 + 8 * b + (e & 7);
+        if (i < k && j < m) out[(int64_t)i * m + j] = v;
+    }
+}
+
+struct GramTmaPlan { int ni, nj, tiles_i, tiles_j, chunks, stages, minb; int64_t rows_per_cta; };
+
+// mode: 1 = deep ring, one CTA per SM; 2 = shallower ring, two CTAs per SM (two consumer warps
+// per scheduler, so one warp's shared-memory reads overlap the other's DMMAs)
+static GramTmaPlan gram_tma_plan(int64_t m, int64_t k, int64_t n, int mode) {
+    GramTmaPlan p;
+    auto frag = [](int64_t v) { return v <= 8 ? 1 : v <= 16 ? 2 : 4; };
+    p.ni = frag(k); p.nj = frag(m);
+    p.tiles_i = (int)((k + 8 * p.ni - 1) / (8 * p.ni));
+    p.tiles_j = (int)((m + 8 * p.nj - 1) / (8 * p.nj));
+    p.minb = mode == 2 ? 2 : 1;
+    p.stages = mode == 2 ? 3 : 5;
+    const int rows = 64 * gt_ksub(p.ni, p.nj);
+    const int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
+    int64_t want = ((int64_t)sm_count() * 2 + tiles - 1) / tiles;        // two CTAs per SM (one or two waves)
+    const int64_t maxc = (n + 8 * rows - 1) / (8 * rows);                // at least 8 stages per CTA
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    int64_t rpc = (n + want - 1) / want;
+    rpc = (rpc + rows - 1) / rows * rows;
+    p.rows_per_cta = rpc;
+    p.chunks = (int)((n + rpc - 1) / rpc);
+    return p;
+}
+
+bool gram_tma_ok(const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo, int64_t k, int64_t n) {
+    return n >= 8192 && n < INT32_MAX && tma_encode_fn() != nullptr && host_aligned16(s) && host_aligned16(o) &&
+           (lds % 2 == 0) && (ldo % 2 == 0);
+}
+
+size_t gram_tma_ws_bytes(int64_t m, int64_t k, int64_t n) {
+    const int c1 = gram_tma_plan(m, k, n, 1).chunks, c2 = gram_tma_plan(m, k, n, 2).chunks;
+    return (size_t)(c1 > c2 ? c1 : c2) * k * m * sizeof(double);
+}
+
+template <int NI, int NJ, bool SAME, int STAGES, int MINB>
+static int gram_tma_launch(const GramTmaPlan& p, const CUtensorMap& mo, const CUtensorMap& ms, int m, int k, int64_t n,
+                           double* part, cudaStream_t st) {
+    constexpr int SMEM = gt_smem(NI, NJ, STAGES);
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(cudaFuncSetAttribute(gram_tma_kernel<NI, NJ, SAME, STAGES, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
+    gram_tma_kernel<NI, NJ, SAME, STAGES, MINB><<<grid, GT_THREADS, SMEM, st>>>(mo, ms, m, k, n, p.rows_per_cta, part);
+    return check_launch();
+}
+
+template <int NI, int NJ>
+static int gram_tma_dispatch(const GramTmaPlan& p, bool same, const CUtensorMap& mo, const CUtensorMap& ms, int m,
+                             int k, int64_t n, double* part, cudaStream_t st) {
+    if (p.minb == 2) {
+        if constexpr (NI == NJ) {
+            if (same) return gram_tma_launch<NI, NJ, true, 3, 2>(p, mo, ms, m, k, n, part, st);
+        }
+        return gram_tma_launch<NI, NJ, false, 3, 2>(p, mo, ms, m, k, n, part, st);
+    }
+    if constexpr (NI == NJ) {
+        if (same) return gram_tma_launch<NI, NJ, true, 5, 1>(p, mo, ms, m, k, n, part, st);
+    }
+    return gram_tma_launch<NI, NJ, false, 5, 1>(p, mo, ms, m, k, n, part, st);
+}
+
+int gram_tma(const double* S, int64_t lds, int64_t m, const double* O, int64_t ldo, int64_t k, int64_t n, double* part,
+             int* chunks_out, int mode, cudaStream_t st) {
+    const GramTmaPlan p = gram_tma_plan(m, k, n, mode);
+    CUtensorMap mo, ms;
+    int rc = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, O, n, k, ldo, 16, 8 * p.ni);
+    if (!rc) rc = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, S, n, m, lds, 16, 8 * p.nj);
+    if (rc) return rc;
+    const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1;
+    *chunks_out = p.chunks;
+    const int im = (int)m, ik = (int)k;
+#define RL_GT(NI_, NJ_) if (p.ni == NI_ && p.nj == NJ_) return gram_tma_dispatch<NI_, NJ_>(p, same, mo, ms, im, ik, n, part, st)
+    RL_GT(4, 4); RL_GT(4, 2); RL_GT(4, 1); RL_GT(2, 4); RL_GT(2, 2); RL_GT(2, 1); RL_GT(1, 4); RL_GT(1, 2); RL_GT(1, 1);
+#undef RL_GT
+    return RL_E_ARG;
+}
+
+}  // namespace rl

@@ -35,14 +35,18 @@ template <typename T, int VG, int SPMM_WARPS>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
-            int m, int cap, int ncols_local, const T* __restrict__ H) {
+            int m, int cap, int ncols_local, const T* __restrict__ H, const int32_t* __restrict__ run_order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* sval = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap;
     int32_t* scol = reinterpret_cast<int32_t*>(reinterpret_cast<T*>(smem_raw) + (size_t)SPMM_WARPS * cap) + (size_t)warp * cap;
 
-    const int64_t row0 = ((int64_t)blockIdx.x * SPMM_WARPS + warp) * 32;
-    if (row0 >= nrows) return;
+    // slot -> 32-row run: identity, or the footprint-clustered order built at set-up
+    // (rl_spmm_cluster_runs): the SPMM_WARPS runs of a CTA then gather from overlapping
+    // column segments, so a line fetched for one warp is an L1 hit for the others
+    const int64_t slot = (int64_t)blockIdx.x * SPMM_WARPS + warp;
+    if (slot * 32 >= nrows) return;
+    const int64_t row0 = (run_order ? (int64_t)__ldg(run_order + slot) : slot) * 32;
     const int64_t r = row0 + lane;
     const bool live = r < nrows;
     const int64_t p0 = live ? __ldg(indptr + r) : 0;
@@ -54,8 +58,8 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
     const bool staged = cnt <= cap;
     if (staged) {
         for (int64_t e = lane; e < cnt; e += 32) {
-            scol[e] = __ldg(indices + base + e);
-            sval[e] = __ldg(values + base + e);
+            scol[e] = ldg_stream(indices + base + e);      // read once: keep L1 for the X gathers
+            sval[e] = ldg_stream(values + base + e);
         }
         __syncwarp();
     }
@@ -113,44 +117,48 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
     }
 }
 
+template <typename T, int W>
+static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indices, const T* values, const T* x,
+                       int64_t ldx, T* y, int64_t ldy, int m, int cap, int ncols_local, const T* halo,
+                       const int32_t* run_order, cudaStream_t st) {
+    constexpr int VG = 8;
+    size_t smem = (size_t)W * cap * (sizeof(T) + 4);
+    auto kern = spmm_kernel<T, VG, W>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    // A/B knob: shared-memory carve-out in percent (the rest of the 256 KB is L1 for the X gathers)
+    static int carveout = 0;
+    if (g_knob[KNOB_SPMM_MODE] != carveout) {
+        carveout = g_knob[KNOB_SPMM_MODE];
+        RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     carveout > 0 ? carveout : cudaSharedmemCarveoutDefault));
+    }
+    int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
+    kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, values, x, ldx, y, ldy, m, cap, ncols_local,
+                                                 halo, run_order);
+    return check_launch();
+}
+
 template <typename T>
 static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
                      const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
-                     cudaStream_t st) {
+                     const int32_t* run_order, int warps, cudaStream_t st) {
     // shared-memory capacity per warp: the average entries of 32 rows + 25 %, in [256, 4096];
     // warps whose segment is longer read the matrix from global memory instead
     int64_t avg = nrows > 0 ? (nnz * 32 + nrows - 1) / nrows : 0;
     int64_t want = (avg * 5 / 4 + 63) / 64 * 64;            // 25 % head room over the average 32-row segment
     int cap = (int)(want < 256 ? 256 : want > 4096 ? 4096 : want);
-    constexpr int VG = 8;
+    if (warps <= 0) warps = g_spmm_warps;
     // big CTAs only when the staged entries of all their warps leave most of L1 free
-    const bool wide = g_spmm_warps >= 16 && (size_t)16 * cap * (sizeof(T) + 4) <= 96 * 1024;
-    if (wide) {
-        constexpr int W = 16;
-        size_t smem = (size_t)W * cap * (sizeof(T) + 4);
-        auto kern = spmm_kernel<T, VG, W>;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
-        kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
-                                                     (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
-    } else {
-        constexpr int W = 4;
-        size_t smem = (size_t)W * cap * (sizeof(T) + 4);
-        auto kern = spmm_kernel<T, VG, W>;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
-        kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx,
-                                                     (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo);
-    }
-    return check_launch();
+    if (warps >= 8 && (size_t)warps * cap * (sizeof(T) + 4) > 96 * 1024) warps = 4;
+#define RL_SPMM_W(W_) return spmm_launch<T, W_>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo, run_order, st)
+    if (warps >= 16) RL_SPMM_W(16);
+    if (warps >= 8) RL_SPMM_W(8);
+    RL_SPMM_W(4);
+#undef RL_SPMM_W
 }
 
 // ---- SELL-32 variant ---------------------------------------------------------------
@@ -288,27 +296,29 @@ int rl_sell_spmm_halo(int dtype, int64_t nrows, int64_t nnz, int64_t nslices, co
     return RL_E_DTYPE;
 }
 
-int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
-                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
-                     int64_t ncols_local, const void* halo, void* stream);
-
-int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
-                const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, void* stream) {
-    return rl_csr_spmm_halo(dtype, nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, 0, nullptr, stream);
-}
-
-int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
-                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
-                     int64_t ncols_local, const void* halo, void* stream) {
+int rl_csr_spmm_ex(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                   const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                   int64_t ncols_local, const void* halo, const int32_t* run_order, int warps, void* stream) {
     if (nrows < 0 || m < 0 || nnz < 0 || m > INT32_MAX || ncols_local > INT32_MAX) return RL_E_ARG;
     if (nrows == 0 || m == 0) return 0;
     if (x == y) return RL_E_ALIAS;
     const double w = dtype == RL_F32 ? 4.0 : 8.0;
     Span span(PK_SPMM, as_stream(stream), nnz * (w + 4.0) + (nrows + 1) * 8.0 + 2.0 * nrows * m * w,
               2.0 * nnz * m);
-    if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
-    if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, as_stream(stream));
+    if (dtype == RL_F32) return spmm_impl<float>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, run_order, warps, as_stream(stream));
+    if (dtype == RL_F64) return spmm_impl<double>(nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, (int)ncols_local, halo, run_order, warps, as_stream(stream));
     return RL_E_DTYPE;
+}
+
+int rl_csr_spmm(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, void* stream) {
+    return rl_csr_spmm_ex(dtype, nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, 0, nullptr, nullptr, 0, stream);
+}
+
+int rl_csr_spmm_halo(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                     const void* values, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m,
+                     int64_t ncols_local, const void* halo, void* stream) {
+    return rl_csr_spmm_ex(dtype, nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, ncols_local, halo, nullptr, 0, stream);
 }
 
 }  // extern "C"

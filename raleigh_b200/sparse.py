@@ -82,6 +82,10 @@ class SparseSymmetricMatrix:
         if self.__plan is None:
             self.__full_diag = full.diagonal()
         self.__sell = _build_sell32(indptr, indices, values)
+        self.__order, self.__warps, self.footprint_ratio = None, 0, None
+        if self.__sell is None and SPMM_CLUSTER_WARPS > 0 and self.__nrows >= 32 * SPMM_CLUSTER_WARPS:
+            order, self.footprint_ratio = cluster_runs(indptr, indices, self.__nrows, SPMM_CLUSTER_WARPS)
+            self.__order, self.__warps = _to_device(order), SPMM_CLUSTER_WARPS
 
     def size(self):
         return self.__n
@@ -122,8 +126,10 @@ class SparseSymmetricMatrix:
             check(lib.rl_sell_spmm_halo(self.__code, self.__nrows, self.__nnz, nsl, sp.ptr, sc.ptr, sv.ptr,
                                         x._wptr(), x._ld, y._wptr(), y._ld, m, ncl, halo, dev.stream()))
             return
-        check(lib.rl_csr_spmm_halo(self.__code, self.__nrows, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
-                                   self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, ncl, halo, dev.stream()))
+        check(lib.rl_csr_spmm_ex(self.__code, self.__nrows, self.__nnz, self.__indptr.ptr, self.__indices.ptr,
+                                 self.__values.ptr, x._wptr(), x._ld, y._wptr(), y._ld, m, ncl, halo,
+                                 self.__order.ptr if self.__order is not None else None, self.__warps,
+                                 dev.stream()))
 
     def _exchange_halo(self, x, m):
         """Pack the boundary rows every peer needs (kernel), all-to-all over NVLink
@@ -143,7 +149,26 @@ class SparseSymmetricMatrix:
         return recv.data_ptr()
 
     def layout(self):
-        return 'sell32' if self.__sell is not None else 'csr'
+        if self.__sell is not None:
+            return 'sell32'
+        return 'csr' if self.__order is None else 'csr+clustered%d' % self.__warps
+
+
+import os as _os
+# 32-row runs per CTA of the staged-CSR kernel, grouped at set-up by shared column footprint
+# (rl_spmm_cluster_runs) so that stencil neighbours in y and z are L1 hits; 0 = consecutive runs
+SPMM_CLUSTER_WARPS = int(_os.environ.get('RALEIGH_B200_SPMM_CLUSTER', '0'))
+
+
+def cluster_runs(indptr, indices, nrows, group):
+    """Footprint-clustered order of the 32-row runs (host set-up, C++ in the library)."""
+    import ctypes
+    nruns = (nrows + 31) // 32
+    order = numpy.empty(nruns, dtype=numpy.int32)
+    ratio = ctypes.c_double()
+    check(lib.rl_spmm_cluster_runs(nrows, dev.host_ptr(indptr), dev.host_ptr(indices), group, dev.host_ptr(order),
+                                   ctypes.byref(ratio)))
+    return order, ratio.value
 
 
 SELL_MAX_PADDING = 1.5     # use SELL-32 only if it stores at most this many times nnz entries
