@@ -142,13 +142,14 @@ class ClockSampler:
 def load_reference_cpu():
     """The reference package with its own CPU algebra (dense_cpu -> dense_numpy,
     MKL being absent); only the SciPy `turbo` shim is applied."""
-    from raleigh_b200.compat import find_reference, shim_scipy
+    from raleigh_b200.compat import find_reference, shim_scipy, unshim_host_hotspots
     path = find_reference()
     if path is None:
         return None
     if path not in sys.path:
         sys.path.insert(0, path)
     shim_scipy()
+    unshim_host_hotspots()      # the GPU arm's vectorised `_norm` must not speed up the reference arm
     return path
 
 

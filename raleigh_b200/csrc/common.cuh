@@ -11,7 +11,7 @@ namespace rl {
 
 extern int64_t g_launches;          // kernels launched by this library (api.cu)
 // A/B knobs set through rl_debug_set_knob (api.cu); 0 = library default everywhere
-enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_MODE = 1, KNOB_SPMM_VG = 2, KNOB_SPMM_ROWS = 3, KNOB_COUNT = 16 };
+enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_MODE = 1, KNOB_SPMM_VG = 2, KNOB_SPMM_ROWS = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_COUNT = 16 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 

@@ -105,7 +105,9 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, int64_t r, i
 template <int NI, int NJ, int JS, bool SAME, int MINB = 1, int DW = GRAM_WARPS>
 __global__ void __launch_bounds__(DW * 32, MINB)
 gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double* __restrict__ O, int64_t ldo,
-                 int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part, int g_pf) {
+                 int k, int64_t n, int64_t rows_per_cta, int fast, double* __restrict__ part, int g_flags) {
+    const int g_pf = g_flags & 255;
+    const bool interleave = (g_flags >> 8) & 1;   // A/B: CTA c owns steps c, c + grid, ... (see gram_tma.cu)
     constexpr int RW = DW / JS;                      // warps interleaving row steps
     constexpr int TILE = JS * NI * NJ * 64;
     extern __shared__ double red_raw[];
@@ -130,23 +132,24 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
 #pragma unroll
         for (int b = 0; b < NJ; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const int64_t c_begin = (int64_t)chunk * rows_per_cta;
-    const int64_t c_end = c_begin + rows_per_cta < n ? c_begin + rows_per_cta : n;
+    const int64_t c_begin = interleave ? (int64_t)chunk * (16 * RW) : (int64_t)chunk * rows_per_cta;
+    const int64_t c_end = interleave ? n : (c_begin + rows_per_cta < n ? c_begin + rows_per_cta : n);
+    const int64_t r_step = interleave ? (int64_t)gridDim.x * (16 * RW) : (int64_t)(16 * RW);
     int64_t r = c_begin + rw * 16;
     // SAME: X.dot(X) with a single tile -- both operands are the same fragments, load once
     if (fast) {
         // full 16-row steps, one 256-bit load per fragment
-        for (; r + 16 <= c_end; r += 16 * RW) {
+        for (; r + 16 <= c_end; r += r_step) {
             double fa[NI][4], fb[NJ][4];
-            if (g_pf > 0 && r + (int64_t)g_pf * 16 * RW + 16 <= c_end) {
+            if (g_pf > 0 && r + (int64_t)g_pf * r_step + 16 <= c_end) {
                 // pull the fragments of a later step into L2 while this one computes
 #pragma unroll
                 for (int t = 0; t < NI; ++t)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(po[t] + r + (int64_t)g_pf * 16 * RW + 4 * c));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(po[t] + r + (int64_t)g_pf * r_step + 4 * c));
                 if (!SAME) {
 #pragma unroll
                     for (int t = 0; t < NJ; ++t)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[t] + r + (int64_t)g_pf * 16 * RW + 4 * c));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps[t] + r + (int64_t)g_pf * r_step + 4 * c));
                 }
             }
 #pragma unroll
@@ -168,7 +171,7 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
                     for (int b = 0; b < NJ; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a][s], fb[b][s]);
         }
     }
-    for (; r < c_end; r += 16 * RW) {   // ragged / unaligned steps
+    for (; r < c_end; r += r_step) {   // ragged / unaligned steps
         double fa[NI][4], fb[NJ][4];
 #pragma unroll
         for (int t = 0; t < NI; ++t) load4<false>(po[t], r + 4 * c, c_end, ai[t], fa[t]);
@@ -280,20 +283,39 @@ gram_simt_kernel(const T* __restrict__ S, int64_t lds, int m, const T* __restric
 }
 
 // ---- second phase: fixed-order sum over the chunk partials ------------------------
-// 8 lanes per output entry: lane l adds chunks l, l+8, ... then a 3-level xor tree.
+// A block owns 32 consecutive entries of G; warp w adds chunks w, w+32, ... (coalesced 256-byte
+// rows, 8 independent loads in flight per lane), then warp 0 adds the 32 warp sums in order.
+// The order depends only on (chunks, km): same bits on every run and every rank.
+constexpr int GRED_U = 8;
 template <typename TA, typename TO>
-__global__ void __launch_bounds__(256) gram_reduce_kernel(const TA* __restrict__ part, int64_t km, int chunks,
-                                                          TO* __restrict__ g) {
-    int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    int l = threadIdx.x & 7;
-    TA acc = TA(0);
-    if (e < km)
-        for (int c = l; c < chunks; c += 8) acc += part[(int64_t)c * km + e];
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (e < km && l == 0) g[e] = (TO)acc;
+__global__ void __launch_bounds__(1024) gram_reduce_kernel(const TA* __restrict__ part, int64_t km, int chunks,
+                                                           TO* __restrict__ g) {
+    __shared__ TA red[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e = (int64_t)blockIdx.x * 32 + lane;
+    TA acc[GRED_U];
+#pragma unroll
+    for (int u = 0; u < GRED_U; ++u) acc[u] = TA(0);
+    if (e < km) {
+        for (int c0 = warp; c0 < chunks; c0 += 32 * GRED_U) {
+#pragma unroll
+            for (int u = 0; u < GRED_U; ++u) {
+                const int c = c0 + 32 * u;
+                if (c < chunks) acc[u] += part[(int64_t)c * km + e];
+            }
+        }
+    }
+    red[warp][lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    __syncthreads();
+    if (warp == 0 && e < km) {
+        TA s = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 32; ++w) s += red[w][lane];
+        g[e] = (TO)s;
+    }
 }
+
+static inline unsigned gram_reduce_blocks(int64_t km) { return (unsigned)((km + 31) / 32); }
 
 template <int NI>
 static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m, const double* O, int64_t ldo,
@@ -301,7 +323,7 @@ static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
     const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1 && p.ni == p.nj && p.js == 1;
 #define RL_GRAM_LAUNCH(NJ_, JS_, SAME_) \
-    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, (GRAM_WARPS / JS_) * JS_ * NI * NJ_ * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch)
+    gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, (GRAM_WARPS / JS_) * JS_ * NI * NJ_ * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch | ((g_knob[KNOB_GRAM_INTERLEAVE] & 1) << 8))
     if (same) {
         RL_GRAM_LAUNCH(NI, 1, true);
     } else if (p.nj == 4 && NI == 4 && p.warps == 8) {
@@ -311,9 +333,9 @@ static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m
             RL_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<NI, 4, 1, false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
             configured = true;
         }
-        gram_dmma_kernel<NI, 4, 1, false, 1, 8><<<grid, 256, smem8, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch);
+        gram_dmma_kernel<NI, 4, 1, false, 1, 8><<<grid, 256, smem8, st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch | ((g_knob[KNOB_GRAM_INTERLEAVE] & 1) << 8));
     } else if (p.nj == 4 && NI == 4 && g_gram_minb == 3) {
-        gram_dmma_kernel<NI, 4, 1, false, 3><<<grid, GRAM_THREADS, 4 * NI * 4 * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch);
+        gram_dmma_kernel<NI, 4, 1, false, 3><<<grid, GRAM_THREADS, 4 * NI * 4 * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch | ((g_knob[KNOB_GRAM_INTERLEAVE] & 1) << 8));
     } else if (p.nj == 4) {
         RL_GRAM_LAUNCH(4, 1, false);
     } else if (p.js == 2) {
@@ -394,7 +416,7 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
         if (tma_mode > 0 && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
             rc = gram_tma((const double*)s, lds, m, (const double*)o, ldo, k, n, (double*)ws, &chunks, tma_mode, st);
             if (rc) return rc;
-            gram_reduce_kernel<double, double><<<(unsigned)((km * 8 + 255) / 256), 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+            gram_reduce_kernel<double, double><<<gram_reduce_blocks(km), 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);
             return check_launch();
         }
         GramPlan p = gram_plan(m, k, n);
@@ -409,28 +431,28 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
         }
         if (rc) return rc;
         chunks = p.chunks;
-        gram_reduce_kernel<double, double><<<(unsigned)((km * 8 + 255) / 256), 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+        gram_reduce_kernel<double, double><<<gram_reduce_blocks(km), 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);
         return check_launch();
     }
     GramPlan p = gram_plan_simt(m, k, n, dtype == RL_F32 ? 4 : 2);
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
     chunks = p.chunks;
-    unsigned rblocks = (unsigned)((km * 8 + 255) / 256);
+    unsigned rblocks = gram_reduce_blocks(km);
     if (dtype == RL_F64) {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 2 == 0) && (ldo % 2 == 0);
         gram_simt_kernel<double, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const double*)s, lds, (int)m, (const double*)o, ldo, (int)k, n, p.rows_per_cta, fast, (double*)ws);
         rc = check_launch(); if (rc) return rc;
-        gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+        gram_reduce_kernel<double, double><<<rblocks, 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);
     } else if (acc64) {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
         gram_simt_kernel<float, double, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_cta, fast, (double*)ws);
         rc = check_launch(); if (rc) return rc;
-        gram_reduce_kernel<double, double><<<rblocks, 256, 0, st>>>((const double*)ws, km, chunks, (double*)g);
+        gram_reduce_kernel<double, double><<<rblocks, 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);
     } else {
         int fast = host_aligned16(s) && host_aligned16(o) && (lds % 4 == 0) && (ldo % 4 == 0);
         gram_simt_kernel<float, float, 8, 8><<<grid, GRAM_THREADS, 0, st>>>((const float*)s, lds, (int)m, (const float*)o, ldo, (int)k, n, p.rows_per_cta, fast, (float*)ws);
         rc = check_launch(); if (rc) return rc;
-        gram_reduce_kernel<float, float><<<rblocks, 256, 0, st>>>((const float*)ws, km, chunks, (float*)g);
+        gram_reduce_kernel<float, float><<<rblocks, 1024, 0, st>>>((const float*)ws, km, chunks, (float*)g);
     }
     return check_launch();
 }

@@ -17,7 +17,10 @@
 
 namespace rl {
 
-constexpr int GT_THREADS = 160;                // 4 consumer warps + 1 producer warp
+constexpr int GT_THREADS = 160;
+#ifndef RL_GRAM_TMA_WAVES
+#define RL_GRAM_TMA_WAVES 1
+#endif                // 4 consumer warps + 1 producer warp
 
 __host__ __device__ constexpr int gt_ksub(int ni, int nj) { return (8 / (ni + nj)) > 0 ? 8 / (ni + nj) : 1; }
 __host__ __device__ constexpr int gt_stage_bytes(int ni, int nj) { return 4 * gt_ksub(ni, nj) * (ni + nj) * 1024; }
@@ -31,7 +34,7 @@ __device__ __forceinline__ void gt_dmma(double& d0, double& d1, double a, double
 template <int NI, int NJ, bool SAME, int STAGES, int MINB>
 __global__ void __launch_bounds__(GT_THREADS, MINB)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_s, int m, int k,
-                int64_t n, int64_t rows_per_cta, double* __restrict__ part) {
+                int64_t n, int64_t rows_per_cta, int interleave, double* __restrict__ part) {
     constexpr int KSUB = gt_ksub(NI, NJ);
     constexpr int OBOX = NI * 1024, SBOX = NJ * 1024, SUB = OBOX + SBOX;
     constexpr int STAGE = gt_stage_bytes(NI, NJ);
@@ -43,9 +46,13 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
     uint64_t* empty = full + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ);
-    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r_end = r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n;
-    const int nstages = (int)((r_end - r_begin + ROWS - 1) / ROWS);
+    // contiguous: CTA c owns rows [c * rows_per_cta, (c+1) * rows_per_cta); interleaved: CTA c owns
+    // stages c, c + grid, c + 2 grid, ... so that the CTAs running at any moment stream one
+    // contiguous region of every vector (whole DRAM pages) instead of grid-many 512-byte pieces
+    const int64_t r_begin = interleave ? (int64_t)blockIdx.x * ROWS : (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_step = interleave ? (int64_t)gridDim.x * ROWS : (int64_t)ROWS;
+    const int64_t r_end = interleave ? n : (r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n);
+    const int nstages = r_begin < r_end ? (int)((r_end - r_begin + r_step - 1) / r_step) : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
@@ -60,7 +67,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = smem + stage * STAGE;
                 mbar_expect_tx(&full[stage], 4 * KSUB * (SAME ? OBOX : SUB));
-                const int64_t r0 = r_begin + (int64_t)it * ROWS;
+                const int64_t r0 = r_begin + (int64_t)it * r_step;
 #pragma unroll
                 for (int q = 0; q < 4 * KSUB; ++q) {
                     // sub-step q = warp * KSUB + u covers rows r0 + 16 q
@@ -146,7 +153,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
     }
 }
 
-struct GramTmaPlan { int ni, nj, tiles_i, tiles_j, chunks, stages, minb; int64_t rows_per_cta; };
+struct GramTmaPlan { int ni, nj, tiles_i, tiles_j, chunks, stages, minb, interleave; int64_t rows_per_cta; };
 
 // mode: 1 = deep ring, one CTA per SM; 2 = shallower ring, two CTAs per SM (two consumer warps
 // per scheduler, so one warp's shared-memory reads overlap the other's DMMAs)
@@ -156,13 +163,20 @@ static GramTmaPlan gram_tma_plan(int64_t m, int64_t k, int64_t n, int mode) {
     p.ni = frag(k); p.nj = frag(m);
     p.tiles_i = (int)((k + 8 * p.ni - 1) / (8 * p.ni));
     p.tiles_j = (int)((m + 8 * p.nj - 1) / (8 * p.nj));
+    p.interleave = (mode & 4) ? 1 : 0;
+    mode &= 3;
     p.minb = mode == 2 ? 2 : 1;
     p.stages = mode == 2 ? 3 : 5;
     const int rows = 64 * gt_ksub(p.ni, p.nj);
     const int64_t tiles = (int64_t)p.tiles_i * p.tiles_j;
-    int64_t want = ((int64_t)sm_count() * 2 + tiles - 1) / tiles;        // two CTAs per SM (one or two waves)
+    // CTAs per SM slot: with one CTA per slot (static partition) ncu shows SMs busy 45..100 % of the
+    // kernel (some SMs are served faster by the memory system); several CTAs per slot let the block
+    // scheduler even that out at the price of one partial tile + ring ramp-up per CTA
+    const int waves = g_knob[KNOB_GRAM_WAVES] > 0 ? g_knob[KNOB_GRAM_WAVES] : RL_GRAM_TMA_WAVES;
+    int64_t want = ((int64_t)sm_count() * 2 * waves + tiles - 1) / tiles;
     const int64_t maxc = (n + 8 * rows - 1) / (8 * rows);                // at least 8 stages per CTA
     if (want > maxc) want = maxc;
+    if (want > (int64_t)sm_count() * 2 * 32) want = (int64_t)sm_count() * 2 * 32;
     if (want < 1) want = 1;
     int64_t rpc = (n + want - 1) / want;
     rpc = (rpc + rows - 1) / rows * rows;
@@ -177,6 +191,8 @@ bool gram_tma_ok(const void* s, int64_t lds, int64_t m, const void* o, int64_t l
 }
 
 size_t gram_tma_ws_bytes(int64_t m, int64_t k, int64_t n) {
+    // for the wave knob in force now (callers size the workspace right before the call; a stale,
+    // smaller workspace is refused with RL_E_WORKSPACE, never overrun)
     const int c1 = gram_tma_plan(m, k, n, 1).chunks, c2 = gram_tma_plan(m, k, n, 2).chunks;
     return (size_t)(c1 > c2 ? c1 : c2) * k * m * sizeof(double);
 }
@@ -192,7 +208,7 @@ static int gram_tma_launch(const GramTmaPlan& p, const CUtensorMap& mo, const CU
         configured = true;
     }
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
-    gram_tma_kernel<NI, NJ, SAME, STAGES, MINB><<<grid, GT_THREADS, SMEM, st>>>(mo, ms, m, k, n, p.rows_per_cta, part);
+    gram_tma_kernel<NI, NJ, SAME, STAGES, MINB><<<grid, GT_THREADS, SMEM, st>>>(mo, ms, m, k, n, p.rows_per_cta, p.interleave, part);
     return check_launch();
 }
 

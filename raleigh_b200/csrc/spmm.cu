@@ -19,20 +19,61 @@ namespace rl {
 // Warps per CTA.  Consecutive rows share gathered lines (stencil neighbours at +-1, +-N):
 // the more consecutive rows a CTA covers, the more of those gathers hit L1 instead of L2.
 // Measured on B200 (profiles/r1c_kernel_tuning.md).
+#ifndef RL_SPMM_WPS_DEFAULT
+#define RL_SPMM_WPS_DEFAULT 24
+#endif
 static int g_spmm_warps = 4;     // 16-warp CTAs measured slower (2.2 vs 3.2 TB/s on 128^3 and 256^3 Laplacians): their staging buffers shrink L1
 
 // Column c of the operator: owned columns come from the local block X (vector-major),
 // halo columns (c >= ncols_local, row-sharded operator) from the exchanged halo buffer H,
 // which is row-interleaved: H[(c - ncols_local) * m + v].
-template <typename T>
-__device__ __forceinline__ T xval(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H, int m,
-                                  int ncols_local, int v, int c) {
-    return (H == nullptr || c < ncols_local) ? __ldg(X + (int64_t)v * ldx + c)
-                                             : __ldg(H + (int64_t)(c - ncols_local) * m + v);
-}
+//
+// Gather addressing: xb[g] = X + (v0 + g) * ldx is hoisted out of the entry loop, so a gather is
+// one IMAD.WIDE (xb[g] + 8c) + one LDG.  (ncu, r1e: with the address of every (vector, column)
+// pair rebuilt from scratch and both the owned and the halo load issued under predicates, the
+// kernel was ISSUE-bound -- 58 % issue slots, 34 % L2, 38 % DRAM -- at ~200 instructions per
+// two entries x 8 vectors instead of ~55.)
+template <typename T, int VG, bool HALO>
+struct Gather {
+    const T* xb[VG];
+    const T* hb;
+    int ncl, m;
+    // pointers of vectors 0..VG-1 (surplus ones alias vector 0: their results are dropped)
+    __device__ __forceinline__ void init(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H, int m_,
+                                         int ncols_local, int v0, int nv) {
+#pragma unroll
+        for (int g = 0; g < VG; ++g) xb[g] = X + (int64_t)(v0 + (g < nv ? g : 0)) * ldx;
+        hb = HALO ? H + v0 : nullptr;
+        ncl = ncols_local;
+        m = m_;
+    }
+    // next group of VG vectors (the last, ragged group re-points its surplus entries)
+    __device__ __forceinline__ void advance(int64_t ldx, int nv_next) {
+#pragma unroll
+        for (int g = 0; g < VG; ++g) xb[g] += (g < nv_next ? (int64_t)VG * ldx : (int64_t)(VG - g) * ldx);
+        if (HALO) hb += VG;
+    }
+    __device__ __forceinline__ void load(int c, T (&x)[VG]) const {
+        if (HALO && c >= ncl) {
+            const T* h = hb + (int64_t)(c - ncl) * m;     // v0 .. v0+VG-1 are contiguous here
+#pragma unroll
+            for (int g = 0; g < VG; ++g) x[g] = __ldg(h + g);
+        } else {
+            // one 64-bit byte offset per entry, one 64-bit add per gather; plain __ldg so that the
+            // compiler keeps hoisting all 2*VG loads above the FMAs (inline-asm loads were sunk next
+            // to their uses: serialised gathers, 0.40 -> 0.58 ms on the 128^3 Laplacian)
+            const int64_t off = (int64_t)c * (int64_t)sizeof(T);
+#pragma unroll
+            for (int g = 0; g < VG; ++g)
+                x[g] = __ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(xb[g]) + off));
+        }
+    }
+};
 
-template <typename T, int VG, int SPMM_WARPS>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+// WPS = resident warps per SM the register allocation is held to (24 -> ~80 registers, 16 -> ~127):
+// with fewer registers ptxas sinks the gathers next to their FMAs and serialises them.
+template <typename T, int VG, int SPMM_WARPS, bool HALO, int WPS>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, WPS / SPMM_WARPS)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
             int m, int cap, int ncols_local, const T* __restrict__ H, const int32_t* __restrict__ run_order) {
@@ -65,48 +106,55 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
     }
     const int q0 = (int)(p0 - base), q1 = (int)(p1 - base);   // valid when staged
 
+    Gather<T, VG, HALO> ga;                         // loop-carried pointers: one per vector of the group
+    ga.init(X, ldx, H, m, ncols_local, 0, m < VG ? m : VG);
     for (int v0 = 0; v0 < m; v0 += VG) {
         T acc[VG];
 #pragma unroll
         for (int g = 0; g < VG; ++g) acc[g] = T(0);
         const int nv = m - v0 < VG ? m - v0 : VG;
-        if (staged) {
-            if (nv == VG) {
-                int p = q0;
-                for (; p + 2 <= q1; p += 2) {
-                    const int c0 = scol[p], c1 = scol[p + 1];
-                    const T a0 = sval[p], a1 = sval[p + 1];
-                    T x0[VG], x1[VG];
+        if (HALO && nv < VG) {
+            // the halo buffer has only m values per column: stay scalar for the ragged last group
+            for (int64_t p = staged ? q0 : p0; p < (staged ? q1 : p1); ++p) {
+                const int c0 = staged ? scol[p] : __ldg(indices + p);
+                const T a0 = staged ? sval[p] : __ldg(values + p);
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) {
-                        x0[g] = xval(X, ldx, H, m, ncols_local, v0 + g, c0);
-                        x1[g] = xval(X, ldx, H, m, ncols_local, v0 + g, c1);
+                for (int g = 0; g < VG; ++g) {
+                    if (g < nv) {
+                        const T xv = c0 < ncols_local ? __ldg(ga.xb[g] + c0)
+                                                      : __ldg(H + (int64_t)(c0 - ncols_local) * m + v0 + g);
+                        acc[g] = fma(a0, xv, acc[g]);
                     }
-#pragma unroll
-                    for (int g = 0; g < VG; ++g) { acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]); }
                 }
-                if (p < q1) {
-                    const int c0 = scol[p];
-                    const T a0 = sval[p];
+            }
+        } else if (staged) {
+            int p = q0;
+#pragma unroll 1
+            for (; p + 2 <= q1; p += 2) {
+                const int c0 = scol[p], c1 = scol[p + 1];
+                const T a0 = sval[p], a1 = sval[p + 1];
+                T x0[VG], x1[VG];
+                ga.load(c0, x0);
+                ga.load(c1, x1);
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
-                }
-            } else {
-                for (int p = q0; p < q1; ++p) {
-                    const int c0 = scol[p];
-                    const T a0 = sval[p];
+                for (int g = 0; g < VG; ++g) { acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]); }
+            }
+            if (p < q1) {
+                const int c0 = scol[p];
+                const T a0 = sval[p];
+                T x0[VG];
+                ga.load(c0, x0);
 #pragma unroll
-                    for (int g = 0; g < VG; ++g)
-                        if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
-                }
+                for (int g = 0; g < VG; ++g) acc[g] = fma(a0, x0[g], acc[g]);
             }
         } else {
             for (int64_t p = p0; p < p1; ++p) {
                 const int c0 = __ldg(indices + p);
                 const T a0 = __ldg(values + p);
+                T x0[VG];
+                ga.load(c0, x0);
 #pragma unroll
-                for (int g = 0; g < VG; ++g)
-                    if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
+                for (int g = 0; g < VG; ++g) acc[g] = fma(a0, x0[g], acc[g]);
             }
         }
         if (live) {
@@ -114,16 +162,18 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
             for (int g = 0; g < VG; ++g)
                 if (g < nv) Y[(int64_t)(v0 + g) * ldy + r] = acc[g];
         }
+        const int left = m - v0 - VG;
+        ga.advance(ldx, left < VG ? (left > 0 ? left : 0) : VG);
     }
 }
 
-template <typename T, int W>
+template <typename T, int W, bool HALO, int WPS>
 static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indices, const T* values, const T* x,
                        int64_t ldx, T* y, int64_t ldy, int m, int cap, int ncols_local, const T* halo,
                        const int32_t* run_order, cudaStream_t st) {
     constexpr int VG = 8;
     size_t smem = (size_t)W * cap * (sizeof(T) + 4);
-    auto kern = spmm_kernel<T, VG, W>;
+    auto kern = spmm_kernel<T, VG, W, HALO, WPS>;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -154,11 +204,17 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     if (warps <= 0) warps = g_spmm_warps;
     // big CTAs only when the staged entries of all their warps leave most of L1 free
     if (warps >= 8 && (size_t)warps * cap * (sizeof(T) + 4) > 96 * 1024) warps = 4;
-#define RL_SPMM_W(W_) return spmm_launch<T, W_>(nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local, (const T*)halo, run_order, st)
+    const bool fat = g_knob[KNOB_SPMM_VG] == 16 || (g_knob[KNOB_SPMM_VG] == 0 && RL_SPMM_WPS_DEFAULT == 16);
+#define RL_SPMM_ARGS nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local
+#define RL_SPMM_W(W_) do { \
+        if (halo) return spmm_launch<T, W_, true, 24>(RL_SPMM_ARGS, (const T*)halo, run_order, st); \
+        if (fat) return spmm_launch<T, W_, false, 16>(RL_SPMM_ARGS, nullptr, run_order, st); \
+        return spmm_launch<T, W_, false, 24>(RL_SPMM_ARGS, nullptr, run_order, st); } while (0)
     if (warps >= 16) RL_SPMM_W(16);
     if (warps >= 8) RL_SPMM_W(8);
     RL_SPMM_W(4);
 #undef RL_SPMM_W
+#undef RL_SPMM_ARGS
 }
 
 // ---- SELL-32 variant ---------------------------------------------------------------
@@ -168,7 +224,7 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
 // and nothing but registers is used -> high occupancy.  A thread keeps up to MT
 // accumulators (one per vector), so for m <= 32 a single pass over the matrix
 // serves the whole block.  Padding entries carry val = 0 and a valid column.
-template <typename T, int MT>
+template <typename T, int MT, bool HALO>
 __global__ void __launch_bounds__(128)
 sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ cols, const T* __restrict__ vals, const T* __restrict__ X, int64_t ldx,
@@ -182,29 +238,38 @@ sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ sli
 #pragma unroll
     for (int g = 0; g < MT; ++g) acc[g] = T(0);
     int64_t p = b0 + lane;
-    if (nv == MT) {
+    Gather<T, MT, HALO> ga;
+    ga.init(X, ldx, H, m, ncols_local, v0, nv);
+    if (!HALO || nv == MT) {
         for (; p + 32 < b1; p += 64) {
-            const int c0 = __ldg(cols + p), c1 = __ldg(cols + p + 32);
-            const T a0 = __ldg(vals + p), a1 = __ldg(vals + p + 32);
+            const int c0 = ldg_stream(cols + p), c1 = ldg_stream(cols + p + 32);
+            const T a0 = ldg_stream(vals + p), a1 = ldg_stream(vals + p + 32);
+            T x0[MT], x1[MT];
+            ga.load(c0, x0);
+            ga.load(c1, x1);
 #pragma unroll
-            for (int g = 0; g < MT; ++g) {
-                acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
-                acc[g] = fma(a1, xval(X, ldx, H, m, ncols_local, v0 + g, c1), acc[g]);
-            }
+            for (int g = 0; g < MT; ++g) { acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]); }
         }
         if (p < b1) {
-            const int c0 = __ldg(cols + p);
-            const T a0 = __ldg(vals + p);
+            const int c0 = ldg_stream(cols + p);
+            const T a0 = ldg_stream(vals + p);
+            T x0[MT];
+            ga.load(c0, x0);
 #pragma unroll
-            for (int g = 0; g < MT; ++g) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
+            for (int g = 0; g < MT; ++g) acc[g] = fma(a0, x0[g], acc[g]);
         }
     } else {
+        // ragged last group of a sharded operator: the halo buffer holds only m values per column
         for (; p < b1; p += 32) {
             const int c0 = __ldg(cols + p);
             const T a0 = __ldg(vals + p);
 #pragma unroll
-            for (int g = 0; g < MT; ++g)
-                if (g < nv) acc[g] = fma(a0, xval(X, ldx, H, m, ncols_local, v0 + g, c0), acc[g]);
+            for (int g = 0; g < MT; ++g) {
+                if (g < nv) {
+                    const T xv = c0 < ncols_local ? __ldg(ga.xb[g] + c0) : __ldg(H + (int64_t)(c0 - ncols_local) * m + v0 + g);
+                    acc[g] = fma(a0, xv, acc[g]);
+                }
+            }
         }
     }
     if (r < nrows) {
@@ -214,29 +279,37 @@ sell_spmm_kernel(int64_t nrows, int64_t nslices, const int64_t* __restrict__ sli
     }
 }
 
-template <typename T>
-static int sell_impl(int64_t nrows, int64_t nslices, const int64_t* slice_ptr, const int32_t* cols, const void* vals,
-                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
-                     cudaStream_t st) {
+template <typename T, bool HALO>
+static int sell_impl_h(int64_t nrows, int64_t nslices, const int64_t* slice_ptr, const int32_t* cols, const void* vals,
+                       const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
+                       cudaStream_t st) {
     const unsigned blocks = (unsigned)((nslices + 3) / 4);
     for (int64_t v0 = 0; v0 < m;) {
         const int64_t left = m - v0;
         int rc;
         if (left > 16) {
             const int nv = left < 32 ? (int)left : 32;
-            sell_spmm_kernel<T, 32><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, nv, (int)m, ncols_local, (const T*)halo);
+            sell_spmm_kernel<T, 32, HALO><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, nv, (int)m, ncols_local, (const T*)halo);
             v0 += nv;
         } else if (left > 8) {
-            sell_spmm_kernel<T, 16><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
+            sell_spmm_kernel<T, 16, HALO><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
             v0 += left;
         } else {
-            sell_spmm_kernel<T, 8><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
+            sell_spmm_kernel<T, 8, HALO><<<blocks, 128, 0, st>>>(nrows, nslices, slice_ptr, cols, (const T*)vals, (const T*)x, ldx, (T*)y, ldy, (int)v0, (int)left, (int)m, ncols_local, (const T*)halo);
             v0 += left;
         }
         rc = check_launch();
         if (rc) return rc;
     }
     return 0;
+}
+
+template <typename T>
+static int sell_impl(int64_t nrows, int64_t nslices, const int64_t* slice_ptr, const int32_t* cols, const void* vals,
+                     const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
+                     cudaStream_t st) {
+    return halo ? sell_impl_h<T, true>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, ncols_local, halo, st)
+                : sell_impl_h<T, false>(nrows, nslices, slice_ptr, cols, vals, x, ldx, y, ldy, m, ncols_local, nullptr, st);
 }
 
 // Halo packing for the row-sharded operator: out[t*m + v] = X[v, idx[t]]

@@ -321,3 +321,57 @@ def test_large_properties(gpu_backend):
     assert np.max(np.abs(Y.dots(Y))) == 0.0
     # determinism: same bits on repeat
     assert np.array_equal(G, X.dot(X))
+
+
+GRAM_TMA_SHAPES = [(32, 8192, 32), (17, 10007, 32), (9, 65539, 5), (40, 20000, 33), (8, 12345, 8), (1, 9000, 32),
+                   (16, 300001, 16)]
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('m,n,k', GRAM_TMA_SHAPES)
+def test_gram_tma_variant_against_oracle(gpu_backend, mode, m, n, k):
+    """The TMA-fed Gram kernel (csrc/gram_tma.cu), forced through the A/B knob: every tile shape,
+    ragged n (TMA zero-fill), offset windows, X.dot(X) with shared fragments, repeatability."""
+    from raleigh_b200._lib import lib
+    rng = np.random.RandomState(m * 100 + k)
+    s = rng.randn(m + 3, n)
+    o = rng.randn(k + 2, n)
+    S, O = gpu_backend.Vectors(s.copy()), gpu_backend.Vectors(o.copy())
+    S.select(m, 3)
+    O.select(k, 2)
+    fac = 10.0 * max(1.0, np.sqrt(n) / 10)
+    lib.rl_debug_set_knob(0, mode)
+    try:
+        g = S.dot(O)
+        close(g, K.gram(s[3:], o[2:]), np.float64, fac)
+        assert np.array_equal(g, S.dot(O))
+        close(S.dot(S), K.gram(s[3:], s[3:]), np.float64, fac)
+    finally:
+        lib.rl_debug_set_knob(0, 0)
+
+
+@pytest.mark.parametrize('group', [4, 8, 16])
+def test_spmm_clustered_run_order_is_bit_identical(gpu_backend, group):
+    """Footprint-clustered CTA composition (rl_spmm_cluster_runs) only permutes which rows a CTA
+    owns: Y must equal the consecutive-run kernel's bit for bit, and the oracle's to rounding."""
+    from raleigh_b200 import sparse as rsp
+    rng = np.random.RandomState(group)
+    for A in (K.lap3d_csr(20, 17, 13), K.lap3d_csr(32, 32, 8)):
+        n = A.shape[0]
+        x = rng.randn(9, n)
+        X = gpu_backend.Vectors(x.copy())
+        saved = rsp.SPMM_CLUSTER_WARPS
+        try:
+            rsp.SPMM_CLUSTER_WARPS = 0
+            op0 = gpu_backend.SparseSymmetricMatrix(A)
+            rsp.SPMM_CLUSTER_WARPS = group
+            op1 = gpu_backend.SparseSymmetricMatrix(A)
+        finally:
+            rsp.SPMM_CLUSTER_WARPS = saved
+        assert op0.layout() == 'csr' and op1.layout() == 'csr+clustered%d' % group
+        assert op1.footprint_ratio < 4.0
+        Y0, Y1 = gpu_backend.Vectors(n, 9), gpu_backend.Vectors(n, 9)
+        op0.apply(X, Y0)
+        op1.apply(X, Y1)
+        assert np.array_equal(Y0.data(), Y1.data())
+        close(Y1.data(), K.sym_spmm(K.sym_upper_csr(A), x), np.float64, 100 * float(abs(A).max()))
