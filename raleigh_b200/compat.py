@@ -104,6 +104,38 @@ def _column_norms(a, axis):
     return numpy.sqrt(numpy.einsum('ij,ij->j' if axis == 0 else 'ij,ij->i', a, a))
 
 
+class _BigLapackProxy:
+    """scipy.linalg for interfaces/partial_svd.py: `_finalize_svd` (partial_svd.py:162-235) factorises
+    nsv x nsv matrices (1000 x 1000 at config 2: eigh, svd, inv) on the host, while the solver's own
+    2m x 2m problems want ONE BLAS thread (256 x 256 LAPACK is slower multi-threaded, which is why the
+    GPU arm runs with the pool limited to 1).  Calls on matrices of order >= 512 get a few threads back
+    for their duration; everything else passes through untouched."""
+    BIG = 512
+
+    def __init__(self, inner, threads):
+        self._inner = inner
+        self._threads = threads
+
+    def __getattr__(self, name):
+        return getattr(self._inner, name)
+
+    def _run(self, fn, a, *args, **kwargs):
+        if self._threads > 1 and getattr(a, 'ndim', 0) == 2 and a.shape[0] >= self.BIG:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=self._threads):
+                return fn(a, *args, **kwargs)
+        return fn(a, *args, **kwargs)
+
+    def svd(self, a, *args, **kwargs):
+        return self._run(self._inner.svd, a, *args, **kwargs)
+
+    def eigh(self, a, *args, **kwargs):
+        return self._run(self._inner.eigh, a, *args, **kwargs)
+
+    def inv(self, a, *args, **kwargs):
+        return self._run(self._inner.inv, a, *args, **kwargs)
+
+
 def shim_host_hotspots():
     """`solver._norm` (solver.py:1745-1746) is `numpy.apply_along_axis(numpy.linalg.norm, ...)`:
     one Python-level call per column, called for every pivot of `_piv_chol` (solver.py:1765-1768)
@@ -116,6 +148,15 @@ def shim_host_hotspots():
     if rsolver._norm is not _column_norms:
         rsolver._reference_norm = rsolver._norm
         rsolver._norm = _column_norms
+    try:
+        import threadpoolctl  # noqa: F401
+        import raleigh.interfaces.partial_svd as psvd
+        threads = int(os.environ.get('RALEIGH_B200_BIG_LAPACK_THREADS', min(4, os.cpu_count() or 1)))
+        if not isinstance(psvd.sla, _BigLapackProxy):
+            psvd._reference_sla = psvd.sla
+            psvd.sla = _BigLapackProxy(psvd.sla, threads)
+    except ImportError:
+        pass
     return True
 
 
@@ -127,6 +168,12 @@ def unshim_host_hotspots():
         return
     if getattr(rsolver, '_reference_norm', None) is not None:
         rsolver._norm = rsolver._reference_norm
+    try:
+        import raleigh.interfaces.partial_svd as psvd
+        if getattr(psvd, '_reference_sla', None) is not None:
+            psvd.sla = psvd._reference_sla
+    except ImportError:
+        pass
 
 
 def install(reference_path=None, sparse=True, dense=True):

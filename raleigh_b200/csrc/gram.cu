@@ -25,7 +25,7 @@ namespace rl {
 
 constexpr int GRAM_WARPS = 4;
 #ifndef RL_GRAM_TMA_DEFAULT
-#define RL_GRAM_TMA_DEFAULT 0   // until measured on B200: register-fragment kernel stays the default
+#define RL_GRAM_TMA_DEFAULT 2   // TMA ring, two CTAs per SM: +7..12 points of HBM peak on single-tile shapes (r1e sweep)
 #endif
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;
 
@@ -413,7 +413,8 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
         // TMA-fed ring variant (gram_tma.cu): KNOB_GRAM_TMA 0 = default policy, -1 = off, 1/2 = forced mode
         const int tma_knob = g_knob[KNOB_GRAM_TMA];
         const int tma_mode = tma_knob > 0 ? tma_knob : (tma_knob == 0 ? RL_GRAM_TMA_DEFAULT : 0);
-        if (tma_mode > 0 && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
+        // multi-tile products (m or k > 32) are DMMA-bound either way: the register kernel stays
+        if (tma_mode > 0 && (tma_knob > 0 || (m <= 32 && k <= 32)) && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
             rc = gram_tma((const double*)s, lds, m, (const double*)o, ldo, k, n, (double*)ws, &chunks, tma_mode, st);
             if (rc) return rc;
             gram_reduce_kernel<double, double><<<gram_reduce_blocks(km), 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);

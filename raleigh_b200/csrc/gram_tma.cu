@@ -19,7 +19,7 @@ namespace rl {
 
 constexpr int GT_THREADS = 160;
 #ifndef RL_GRAM_TMA_WAVES
-#define RL_GRAM_TMA_WAVES 1
+#define RL_GRAM_TMA_WAVES 4
 #endif                // 4 consumer warps + 1 producer warp
 
 __host__ __device__ constexpr int gt_ksub(int ni, int nj) { return (8 / (ni + nj)) > 0 ? 8 / (ni + nj) : 1; }
@@ -157,7 +157,7 @@ struct GramTmaPlan { int ni, nj, tiles_i, tiles_j, chunks, stages, minb, interle
 
 // mode: 1 = deep ring, one CTA per SM; 2 = shallower ring, two CTAs per SM (two consumer warps
 // per scheduler, so one warp's shared-memory reads overlap the other's DMMAs)
-static GramTmaPlan gram_tma_plan(int64_t m, int64_t k, int64_t n, int mode) {
+static GramTmaPlan gram_tma_plan(int64_t m, int64_t k, int64_t n, int mode, bool same = false) {
     GramTmaPlan p;
     auto frag = [](int64_t v) { return v <= 8 ? 1 : v <= 16 ? 2 : 4; };
     p.ni = frag(k); p.nj = frag(m);
@@ -172,7 +172,10 @@ static GramTmaPlan gram_tma_plan(int64_t m, int64_t k, int64_t n, int mode) {
     // CTAs per SM slot: with one CTA per slot (static partition) ncu shows SMs busy 45..100 % of the
     // kernel (some SMs are served faster by the memory system); several CTAs per slot let the block
     // scheduler even that out at the price of one partial tile + ring ramp-up per CTA
-    const int waves = g_knob[KNOB_GRAM_WAVES] > 0 ? g_knob[KNOB_GRAM_WAVES] : RL_GRAM_TMA_WAVES;
+    // measured (profiles/r1e_gram_spmm.md): 4 CTAs per slot pay off only for the DMMA-heavy tiles
+    // (32x32, 32x16) of X^T Y; X^T X and the small tiles are fastest with the static partition
+    const int waves = g_knob[KNOB_GRAM_WAVES] > 0 ? g_knob[KNOB_GRAM_WAVES]
+                                                  : ((p.ni + p.nj >= 6 && !same) ? RL_GRAM_TMA_WAVES : 1);
     int64_t want = ((int64_t)sm_count() * 2 * waves + tiles - 1) / tiles;
     const int64_t maxc = (n + 8 * rows - 1) / (8 * rows);                // at least 8 stages per CTA
     if (want > maxc) want = maxc;
@@ -229,12 +232,12 @@ static int gram_tma_dispatch(const GramTmaPlan& p, bool same, const CUtensorMap&
 
 int gram_tma(const double* S, int64_t lds, int64_t m, const double* O, int64_t ldo, int64_t k, int64_t n, double* part,
              int* chunks_out, int mode, cudaStream_t st) {
-    const GramTmaPlan p = gram_tma_plan(m, k, n, mode);
+    const bool same = S == O && lds == ldo && m == k && m <= 32;
+    const GramTmaPlan p = gram_tma_plan(m, k, n, mode, same);
     CUtensorMap mo, ms;
     int rc = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, O, n, k, ldo, 16, 8 * p.ni);
     if (!rc) rc = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, S, n, m, lds, 16, 8 * p.nj);
     if (rc) return rc;
-    const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1;
     *chunks_out = p.chunks;
     const int im = (int)m, ik = (int)k;
 #define RL_GT(NI_, NJ_) if (p.ni == NI_ && p.nj == NJ_) return gram_tma_dispatch<NI_, NJ_>(p, same, mo, ms, im, ik, n, part, st)

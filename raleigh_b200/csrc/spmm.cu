@@ -72,7 +72,7 @@ struct Gather {
 
 // WPS = resident warps per SM the register allocation is held to (24 -> ~80 registers, 16 -> ~127):
 // with fewer registers ptxas sinks the gathers next to their FMAs and serialises them.
-template <typename T, int VG, int SPMM_WARPS, bool HALO, int WPS>
+template <typename T, int VG, int SPMM_WARPS, bool HALO, int WPS, int NB>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, WPS / SPMM_WARPS)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
@@ -129,6 +129,24 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
             }
         } else if (staged) {
             int p = q0;
+            if (NB == 4) {
+                // four entries per step: 4 * VG gathers in flight per lane
+#pragma unroll 1
+                for (; p + 4 <= q1; p += 4) {
+                    T x0[VG], x1[VG], x2[VG], x3[VG];
+                    const int c0 = scol[p], c1 = scol[p + 1], c2 = scol[p + 2], c3 = scol[p + 3];
+                    ga.load(c0, x0);
+                    ga.load(c1, x1);
+                    ga.load(c2, x2);
+                    ga.load(c3, x3);
+                    const T a0 = sval[p], a1 = sval[p + 1], a2 = sval[p + 2], a3 = sval[p + 3];
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) {
+                        acc[g] = fma(a0, x0[g], acc[g]); acc[g] = fma(a1, x1[g], acc[g]);
+                        acc[g] = fma(a2, x2[g], acc[g]); acc[g] = fma(a3, x3[g], acc[g]);
+                    }
+                }
+            }
 #pragma unroll 1
             for (; p + 2 <= q1; p += 2) {
                 const int c0 = scol[p], c1 = scol[p + 1];
@@ -167,13 +185,13 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
     }
 }
 
-template <typename T, int W, bool HALO, int WPS>
+template <typename T, int W, bool HALO, int WPS, int NB>
 static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indices, const T* values, const T* x,
                        int64_t ldx, T* y, int64_t ldy, int m, int cap, int ncols_local, const T* halo,
                        const int32_t* run_order, cudaStream_t st) {
     constexpr int VG = 8;
     size_t smem = (size_t)W * cap * (sizeof(T) + 4);
-    auto kern = spmm_kernel<T, VG, W, HALO, WPS>;
+    auto kern = spmm_kernel<T, VG, W, HALO, WPS, NB>;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -207,9 +225,9 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     const bool fat = g_knob[KNOB_SPMM_VG] == 16 || (g_knob[KNOB_SPMM_VG] == 0 && RL_SPMM_WPS_DEFAULT == 16);
 #define RL_SPMM_ARGS nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local
 #define RL_SPMM_W(W_) do { \
-        if (halo) return spmm_launch<T, W_, true, 24>(RL_SPMM_ARGS, (const T*)halo, run_order, st); \
-        if (fat) return spmm_launch<T, W_, false, 16>(RL_SPMM_ARGS, nullptr, run_order, st); \
-        return spmm_launch<T, W_, false, 24>(RL_SPMM_ARGS, nullptr, run_order, st); } while (0)
+        if (halo) return spmm_launch<T, W_, true, 24, 2>(RL_SPMM_ARGS, (const T*)halo, run_order, st); \
+        if (fat) return spmm_launch<T, W_, false, 16, 4>(RL_SPMM_ARGS, nullptr, run_order, st); \
+        return spmm_launch<T, W_, false, 24, 2>(RL_SPMM_ARGS, nullptr, run_order, st); } while (0)
     if (warps >= 16) RL_SPMM_W(16);
     if (warps >= 8) RL_SPMM_W(8);
     RL_SPMM_W(4);

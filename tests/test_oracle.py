@@ -268,3 +268,19 @@ def test_host_hotspot_shim_matches_reference_norm_and_piv_chol(ref_root):
     factor(96, 32, 50)       # rank deficient: columns are dropped
     factor(40, 0, 40)
     assert rs._norm is ref_norm
+    # the big-LAPACK thread proxy of partial_svd is transparent and removable
+    import scipy.linalg as sla
+    import raleigh.interfaces.partial_svd as psvd
+    compat.shim_host_hotspots()
+    try:
+        assert isinstance(psvd.sla, compat._BigLapackProxy)
+        g = rng.randn(600, 600)
+        g = g @ g.T + 600 * np.eye(600)
+        w0 = sla.eigh(g, eigvals_only=True)
+        w1 = psvd.sla.eigh(g, eigvals_only=True)
+        assert np.allclose(w0, w1, rtol=1e-12)
+        assert np.allclose(psvd.sla.inv(g) @ g, np.eye(600), atol=1e-9)
+        assert psvd.sla.norm is sla.norm
+    finally:
+        compat.unshim_host_hotspots()
+    assert not isinstance(psvd.sla, compat._BigLapackProxy)

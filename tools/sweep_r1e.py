@@ -28,7 +28,7 @@ from microbench import timeit, peak_gbs  # noqa: E402
 from run_c4 import lap3d_slab  # noqa: E402
 
 KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 4, 5
-GRAM_MODES = [(-1, 1), (2, 1), (2, 2), (2, 4), (2, 6), (2, 8), (2, 12), (2, 16), (1, 8)]      # (TMA mode, CTAs per SM slot)
+GRAM_MODES = [(-1, 0), (0, 0), (2, 1), (2, 3), (2, 4), (2, 5)]      # (TMA mode, CTAs per SM slot)
 OUT = [None]
 
 
@@ -214,7 +214,7 @@ if __name__ == '__main__':
     if 'edge' in only:
         gram_edge_checks()
     if 'gram' in only:
-        gram_sweep(2097152, [(32, 32), (16, 16), (8, 8), (32, 16)], args.reps)
+        gram_sweep(2097152, [(32, 32), (16, 16), (8, 8), (32, 16), (32, 8), (24, 24), (64, 64)], args.reps)
         gram_sweep(140874, [(32, 32)], args.reps)
         gram_sweep(32768, [(16, 16)], args.reps)
     if 'spmm' in only:
