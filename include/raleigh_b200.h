@@ -188,6 +188,12 @@ int rl_dense_apply_tc(const void* a, const void* a_lo, int64_t lda, int64_t M, i
                       const void* x, int64_t ldx, void* y, int64_t ldy, int64_t k, int transp,
                       double alpha, double beta, void* ws, size_t ws_bytes, void* stream);
 
+/* AMatrix.__init__ dense_matrix.py:32-34 scans the host array with numpy.amin / numpy.amax for
+ * scale(); the same two numbers from the device copy in one HBM-bound pass (host scalars of the
+ * block's dtype; NaNs are ignored where NumPy would propagate them). */
+int rl_minmax_h(int dtype, const void* x, int64_t ld, int64_t m, int64_t n, void* min_h, void* max_h,
+                void* stream);
+
 /* ---- sparse symmetric operator ------------------------------------------- */
 /* SparseSymmetricMatrix.apply sparse_mkl.py:42-48 -> mkl_?csrmm mkl_wrap.py:274-276
  * (and mkl_?csrsymv :261-262 for m == 1).  The device holds the FULL symmetric

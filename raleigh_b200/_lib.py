@@ -77,6 +77,7 @@ PROTOTYPES = {
     'rl_split_tf32': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     'rl_dense_apply_tc': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_int,
                                   c_dbl, c_dbl, c_vp, c_sz, c_vp]),
+    'rl_minmax_h': (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'rl_csr_spmm': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     'rl_csr_spmm_ex': (c_int, [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp,
                                c_vp, c_int, c_vp]),

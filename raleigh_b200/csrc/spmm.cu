@@ -76,7 +76,8 @@ template <typename T, int VG, int SPMM_WARPS, bool HALO, int WPS, int NB>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, WPS / SPMM_WARPS)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
-            int m, int cap, int ncols_local, const T* __restrict__ H, const int32_t* __restrict__ run_order) {
+            int m, int cap, int ncols_local, const T* __restrict__ H, const int32_t* __restrict__ run_order,
+            int pf_last) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* sval = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap;
@@ -105,6 +106,17 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
         __syncwarp();
     }
     const int q0 = (int)(p0 - base), q1 = (int)(p1 - base);   // valid when staged
+
+    // A/B (KNOB_SPMM_ROWS = 1): rows are processed in increasing order, so the LARGEST column of a row
+    // (the +N^2 neighbour of a stencil) is usually a first touch that waits for DRAM; pull those lines
+    // of every vector into L2 now, one warp-wide request per vector, before the gathers reach them
+    if (pf_last && staged && live && q1 > q0) {
+        const int cl = scol[q1 - 1];
+        if (!HALO || cl < ncols_local) {
+            const T* px = X + cl;
+            for (int v = 0; v < m; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)v * ldx));
+        }
+    }
 
     Gather<T, VG, HALO> ga;                         // loop-carried pointers: one per vector of the group
     ga.init(X, ldx, H, m, ncols_local, 0, m < VG ? m : VG);
@@ -206,7 +218,7 @@ static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indi
     }
     int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, values, x, ldx, y, ldy, m, cap, ncols_local,
-                                                 halo, run_order);
+                                                 halo, run_order, g_knob[KNOB_SPMM_ROWS] == 1);
     return check_launch();
 }
 

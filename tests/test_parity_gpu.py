@@ -375,3 +375,31 @@ def test_spmm_clustered_run_order_is_bit_identical(gpu_backend, group):
         op1.apply(X, Y1)
         assert np.array_equal(Y0.data(), Y1.data())
         close(Y1.data(), K.sym_spmm(K.sym_upper_csr(A), x), np.float64, 100 * float(abs(A).max()))
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_matrix_minmax_and_amatrix_scale(gpu_backend, dtype, ref_root):
+    """rl_minmax_h against numpy.amin/amax (C and F order, padded leading dimension, negative
+    extremes), and the reference's own AMatrix.scale() (dense_matrix.py:32-34, :63-64) served from
+    the device copy through compat's numpy proxy."""
+    from raleigh_b200 import vectors as rv
+    rng = np.random.RandomState(3)
+    for shape in ((1, 1), (3, 1001), (257, 130), (64, 70000)):
+        a = (rng.randn(*shape) * 3).astype(dtype)
+        a[-1, -1] = -50.0
+        a[0, shape[1] // 2] = 40.0
+        for arr in (a, np.asfortranarray(a)):
+            lo, hi = gpu_backend.Matrix(arr).minmax()
+            assert lo == np.amin(a) == -50.0 and hi == np.amax(a) == 40.0
+    gpu_backend.install(ref_root)
+    from raleigh.algebra.dense_matrix import AMatrix
+    saved = rv.MINMAX_ON_DEVICE_BYTES
+    rv.MINMAX_ON_DEVICE_BYTES = 0
+    try:
+        a = rng.randn(300, 200).astype(dtype)
+        am = AMatrix(a, arch='gpu!')
+        assert am.scale() == max(abs(a.min()), abs(a.max()))
+        assert not rv._recent_uploads                  # entry consumed by the amin/amax pair
+        assert np.amin(a) == a.min()
+    finally:
+        rv.MINMAX_ON_DEVICE_BYTES = saved

@@ -27,7 +27,7 @@ from raleigh_b200 import sparse as rsp  # noqa: E402
 from microbench import timeit, peak_gbs  # noqa: E402
 from run_c4 import lap3d_slab  # noqa: E402
 
-KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 4, 5
+KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_SPMM_PF, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 3, 4, 5
 GRAM_MODES = [(-1, 0), (0, 0), (2, 1), (2, 3), (2, 4), (2, 5)]      # (TMA mode, CTAs per SM slot)
 OUT = [None]
 
@@ -104,9 +104,10 @@ def ncu_pass(N):
     ip, ix, va = _priv(op, 'indptr'), _priv(op, 'indices'), _priv(op, 'values')
     X, Y = rb.Vectors(n, m), rb.Vectors(n, m)
     X.fill_random_device(3)
-    for group, wps in ((0, 24), (4, 24), (4, 16), (8, 16)):
+    for group, wps, pf in ((0, 24, 0), (0, 24, 1), (4, 24, 1), (0, 16, 1)):
         ob = None
         lib.rl_debug_set_knob(KNOB_SPMM_WPS, wps)
+        lib.rl_debug_set_knob(KNOB_SPMM_PF, pf)
         if group:
             ob = rsp._to_device(rsp.cluster_runs(indptr, indices, n, group)[0])
         check(lib.rl_csr_spmm_ex(1, n, op.nnz(), ip.ptr, ix.ptr, va.ptr, X._wptr(), X._ld, Y._wptr(), Y._ld, m, 0, None,
@@ -171,8 +172,9 @@ def spmm_sweep(name, A_full, plans, reps):
                 orders[group] = (rsp._to_device(order), ratio, time.time() - t1)
             order_buf, ratio, cl_s = orders[group]
         warps = group if group else 4
-        for carve in carveouts:
+        for (carve, pf) in carveouts:
             lib.rl_debug_set_knob(KNOB_SPMM_WPS, carve)
+            lib.rl_debug_set_knob(KNOB_SPMM_PF, pf)
             f = lambda: check(lib.rl_csr_spmm_ex(1, n, nnz, ip.ptr, ix.ptr, va.ptr, X._wptr(), X._ld, Y._wptr(), Y._ld, m,
                                                  0, None, order_buf.ptr if order_buf else None, warps, dev.stream()))
             Y.zero()
@@ -187,11 +189,12 @@ def spmm_sweep(name, A_full, plans, reps):
                 d = Y.dots(Y)
                 diff = float(np.abs(d).max())
             ms, best = timeit(f, reps=reps)
-            emit(exp='spmm', matrix=name, n=n, nnz=nnz, m=m, group=group, warps=warps, wps=carve,
+            emit(exp='spmm', matrix=name, n=n, nnz=nnz, m=m, group=group, warps=warps, wps=carve, pf=pf,
                  footprint_ratio=ratio, cluster_setup_s=round(cl_s, 3), ms=round(ms, 5), ms_best=round(best, 5),
                  GBps=round(byts / ms / 1e6, 1), frac_hbm=round(byts / ms / 1e6 / peak_gbs(), 3),
                  sq_diff_vs_default=diff)
       lib.rl_debug_set_knob(KNOB_SPMM_WPS, 0)
+      lib.rl_debug_set_knob(KNOB_SPMM_PF, 0)
       if op.layout() == 'sell32':
         ms, best = timeit(lambda: op.apply(X, Y), reps=reps)
         emit(exp='spmm', matrix=name, n=n, nnz=nnz, m=m, group='sell32', ms=round(ms, 5), GBps=round(byts / ms / 1e6, 1),
@@ -220,9 +223,9 @@ if __name__ == '__main__':
     if 'spmm' in only:
         N = args.N
         spmm_sweep('lap3d_%d' % N, lap3d_slab(N, 0, N ** 3),
-                   [(32, (0, 4, 8, 16), (24, 16)), (16, (0, 4, 8), (24, 16)), (8, (0, 4, 8), (24, 16))], args.reps)
-        spmm_sweep('lap3d_32', lap3d_slab(32, 0, 32 ** 3), [(16, (0, 4, 8), (24, 16))], args.reps)
+                   [(32, (0, 4, 8), ((24, 0), (24, 1), (16, 0), (16, 1))), (16, (0, 4), ((24, 0), (24, 1))), (8, (0,), ((24, 0), (24, 1)))], args.reps)
+        spmm_sweep('lap3d_32', lap3d_slab(32, 0, 32 ** 3), [(16, (0, 4), ((24, 0), (24, 1)))], args.reps)
         from tests_common import spd_c3_like
         offs = tuple(sorted(set([1, 2, 3, 4, 5, 6, 440, 441, 442, 443, 444, 445, 446, 2656, 2657, 2658, 2659, 2660,
                                  2661, 2662, 2214, 2215, 2216, 2217, 3100, 3101, 3102])))
-        spmm_sweep('c3like_55nnz', spd_c3_like(140874, offsets=offs), [(32, (0, 4), (24, 16))], args.reps)
+        spmm_sweep('c3like_55nnz', spd_c3_like(140874, offsets=offs), [(32, (0,), ((24, 0), (24, 1), (16, 0), (16, 1)))], args.reps)
