@@ -234,7 +234,9 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     if (warps <= 0) warps = g_spmm_warps;
     // big CTAs only when the staged entries of all their warps leave most of L1 free
     if (warps >= 8 && (size_t)warps * cap * (sizeof(T) + 4) > 96 * 1024) warps = 4;
-    const bool fat = g_knob[KNOB_SPMM_VG] == 16 || (g_knob[KNOB_SPMM_VG] == 0 && RL_SPMM_WPS_DEFAULT == 16);
+    // long rows (>= 16 entries on average): four entries x 8 vectors in flight per lane and the
+    // 127-register budget win (55 nnz/row: 0.24 -> 0.16 ms); stencils keep 24 warps per SM
+    const bool fat = g_knob[KNOB_SPMM_VG] == 16 || (g_knob[KNOB_SPMM_VG] == 0 && nnz >= 16 * nrows);
 #define RL_SPMM_ARGS nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local
 #define RL_SPMM_W(W_) do { \
         if (halo) return spmm_launch<T, W_, true, 24, 2>(RL_SPMM_ARGS, (const T*)halo, run_order, st); \

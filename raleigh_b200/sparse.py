@@ -81,7 +81,7 @@ class SparseSymmetricMatrix:
         self.__values = _to_device(values)
         if self.__plan is None:
             self.__full_diag = full.diagonal()
-        self.__sell = _build_sell32(indptr, indices, values)
+        self.__sell = _build_sell32(indptr, indices, values) if SPMM_LAYOUT == 'sell' else None
         self.__order, self.__warps, self.footprint_ratio = None, 0, None
         if self.__sell is None and SPMM_CLUSTER_WARPS > 0 and self.__nrows >= 32 * SPMM_CLUSTER_WARPS:
             order, self.footprint_ratio = cluster_runs(indptr, indices, self.__nrows, SPMM_CLUSTER_WARPS)
@@ -158,6 +158,9 @@ import os as _os
 # 32-row runs per CTA of the staged-CSR kernel, grouped at set-up by shared column footprint
 # (rl_spmm_cluster_runs) so that stencil neighbours in y and z are L1 hits; 0 = consecutive runs
 SPMM_CLUSTER_WARPS = int(_os.environ.get('RALEIGH_B200_SPMM_CLUSTER', '0'))
+# 'csr' (default: staged-CSR kernel, r1e: faster than SELL-32 on every matrix measured once its gather
+# addressing was fixed) or 'sell' (SELL-32 when the padding rule below allows it)
+SPMM_LAYOUT = _os.environ.get('RALEIGH_B200_SPMM_LAYOUT', 'csr')
 
 
 def cluster_runs(indptr, indices, nrows, group):
@@ -172,10 +175,10 @@ def cluster_runs(indptr, indices, nrows, group):
 
 
 SELL_MAX_PADDING = 1.5     # use SELL-32 only if it stores at most this many times nnz entries
-SELL_MIN_ROW_NNZ = 24      # ... and rows are long: measured on B200 (profiles/r1c_kernel_tuning.md) the
-                           # staged-CSR kernel wins on stencils (7 nnz/row: 3.7 vs 1.9 TB/s, its 8-vector
-                           # groups keep the gathered lines L1-resident), SELL-32 with 32 accumulators
-                           # wins at 55 nnz/row (0.67 vs 0.38 TB/s, matrix streamed once)
+SELL_MIN_ROW_NNZ = 24      # ... and rows are long.  History (profiles/r1c_kernel_tuning.md, r1e_gram_spmm.md):
+                           # SELL-32 used to win at 55 nnz/row (0.67 vs 0.38 TB/s); with hoisted gather
+                           # addressing both kernels got faster and staged CSR with 4-entry batches leads
+                           # (1.03 vs 0.90 TB/s), so SELL-32 is opt-in (RALEIGH_B200_SPMM_LAYOUT=sell)
 
 
 def _build_sell32(indptr, indices, values):

@@ -403,3 +403,32 @@ def test_matrix_minmax_and_amatrix_scale(gpu_backend, dtype, ref_root):
         assert np.amin(a) == a.min()
     finally:
         rv.MINMAX_ON_DEVICE_BYTES = saved
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_spmm_long_rows_csr_batches_and_sell_layout(gpu_backend, dtype):
+    """>= 16 entries per row: the staged-CSR kernel switches to 4-entry batches (127-register
+    budget); the opt-in SELL-32 layout must give the same product.  Odd vector counts exercise the
+    ragged last group of both."""
+    from raleigh_b200 import sparse as rsp
+    from tests_common import spd_c3_like
+    offs = (1, 2, 3, 4, 5, 6, 40, 41, 42, 43, 44, 45, 46, 300, 301, 302, 303)
+    A = spd_c3_like(3000, offsets=offs).astype(dtype)
+    assert A.nnz >= 24 * A.shape[0]
+    rng = np.random.RandomState(8)
+    saved = rsp.SPMM_LAYOUT
+    try:
+        ops = []
+        for layout in ('csr', 'sell'):
+            rsp.SPMM_LAYOUT = layout
+            ops.append(gpu_backend.SparseSymmetricMatrix(A))
+    finally:
+        rsp.SPMM_LAYOUT = saved
+    assert ops[0].layout() == 'csr' and ops[1].layout() == 'sell32'
+    for m in (1, 8, 13, 32, 35):
+        x = rng.randn(m, 3000).astype(dtype)
+        ref = K.sym_spmm(K.sym_upper_csr(A), x)
+        for op in ops:
+            X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(3000, m, dtype)
+            op.apply(X, Y)
+            close(Y.data(), ref, dtype, 100 * float(abs(A).max()))
