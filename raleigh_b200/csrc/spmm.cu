@@ -19,6 +19,9 @@ namespace rl {
 // Warps per CTA.  Consecutive rows share gathered lines (stencil neighbours at +-1, +-N):
 // the more consecutive rows a CTA covers, the more of those gathers hit L1 instead of L2.
 // Measured on B200 (profiles/r1c_kernel_tuning.md).
+#ifndef RL_SPMM_PF_DEFAULT
+#define RL_SPMM_PF_DEFAULT 1      // bit 0 measured: 0.381 -> 0.330 ms on the 128^3 Laplacian (m = 32)
+#endif
 #ifndef RL_SPMM_WPS_DEFAULT
 #define RL_SPMM_WPS_DEFAULT 24
 #endif
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, WPS / SPMM_WARPS)
 spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
             const T* __restrict__ values, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy,
             int m, int cap, int ncols_local, const T* __restrict__ H, const int32_t* __restrict__ run_order,
-            int pf_last) {
+            int pf_mode, int pf_dist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* sval = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cap;
@@ -107,14 +110,33 @@ spmm_kernel(int64_t nrows, const int64_t* __restrict__ indptr, const int32_t* __
     }
     const int q0 = (int)(p0 - base), q1 = (int)(p1 - base);   // valid when staged
 
-    // A/B (KNOB_SPMM_ROWS = 1): rows are processed in increasing order, so the LARGEST column of a row
-    // (the +N^2 neighbour of a stencil) is usually a first touch that waits for DRAM; pull those lines
-    // of every vector into L2 now, one warp-wide request per vector, before the gathers reach them
-    if (pf_last && staged && live && q1 > q0) {
+    // L2 prefetch (ncu, r1e: half of the gathers' L2 lookups missed although DRAM reads X once --
+    // they waited for lines still in flight from DRAM).  Rows are processed in increasing order, so
+    //  bit 0: the LARGEST column of a row (the +N^2 neighbour of a stencil) is usually a first touch:
+    //         pull those lines of every vector into L2 now, one warp-wide request per vector;
+    //  bit 1: the CSR entries of the run that will start when this one retires (pf_dist slots ahead)
+    //         are a cold DRAM read in front of two dependent round trips: pull them in as well;
+    //  bit 2: also the same X lines shifted by pf_dist runs (banded matrices: column ~ row + const).
+    if (pf_mode && staged && live && q1 > q0) {
         const int cl = scol[q1 - 1];
-        if (!HALO || cl < ncols_local) {
+        if ((pf_mode & 1) && (!HALO || cl < ncols_local)) {
             const T* px = X + cl;
             for (int v = 0; v < m; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)v * ldx));
+        }
+        if (pf_mode & 4) {
+            const int64_t cf = (int64_t)cl + (int64_t)pf_dist * 32;
+            if (cf < (HALO ? (int64_t)ncols_local : nrows)) {
+                const T* px = X + cf;
+                for (int v = 0; v < m; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)v * ldx));
+            }
+        }
+    }
+    if ((pf_mode & 2) && run_order == nullptr) {
+        const int64_t fr = (slot + pf_dist) * 32;
+        if (fr + 32 <= nrows) {
+            const int64_t f0 = __ldg(indptr + fr), f1 = __ldg(indptr + fr + 32);
+            for (int64_t e = f0 + lane * 32; e < f1; e += 1024) asm volatile("prefetch.global.L2 [%0];" ::"l"(indices + e));
+            for (int64_t e = f0 + lane * 16; e < f1; e += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(values + e));
         }
     }
 
@@ -218,7 +240,9 @@ static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indi
     }
     int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, values, x, ldx, y, ldy, m, cap, ncols_local,
-                                                 halo, run_order, g_knob[KNOB_SPMM_ROWS] == 1);
+                                                 halo, run_order,
+                                                 g_knob[KNOB_SPMM_ROWS] > 0 ? g_knob[KNOB_SPMM_ROWS] : (g_knob[KNOB_SPMM_ROWS] < 0 ? 0 : RL_SPMM_PF_DEFAULT),
+                                                 sm_count() * WPS);
     return check_launch();
 }
 

@@ -327,7 +327,7 @@ GRAM_TMA_SHAPES = [(32, 8192, 32), (17, 10007, 32), (9, 65539, 5), (40, 20000, 3
                    (16, 300001, 16)]
 
 
-@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('mode', [1, 2, 3])
 @pytest.mark.parametrize('m,n,k', GRAM_TMA_SHAPES)
 def test_gram_tma_variant_against_oracle(gpu_backend, mode, m, n, k):
     """The TMA-fed Gram kernel (csrc/gram_tma.cu), forced through the A/B knob: every tile shape,
@@ -384,7 +384,9 @@ def test_matrix_minmax_and_amatrix_scale(gpu_backend, dtype, ref_root):
     the device copy through compat's numpy proxy."""
     from raleigh_b200 import vectors as rv
     rng = np.random.RandomState(3)
-    for shape in ((1, 1), (3, 1001), (257, 130), (64, 70000)):
+    one = gpu_backend.Matrix(np.full((1, 1), -7.0, dtype=dtype)).minmax()
+    assert one[0] == one[1] == -7.0
+    for shape in ((1, 2), (3, 1001), (257, 130), (64, 70000)):
         a = (rng.randn(*shape) * 3).astype(dtype)
         a[-1, -1] = -50.0
         a[0, shape[1] // 2] = 40.0

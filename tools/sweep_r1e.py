@@ -28,7 +28,7 @@ from microbench import timeit, peak_gbs  # noqa: E402
 from run_c4 import lap3d_slab  # noqa: E402
 
 KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_SPMM_PF, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 3, 4, 5
-GRAM_MODES = [(-1, 0), (0, 0), (2, 1), (2, 3), (2, 4), (2, 5)]      # (TMA mode, CTAs per SM slot)
+GRAM_MODES = [(-1, 0), (0, 0), (3, 4), (3, 8), (3, 16), (3, 32)]      # (TMA mode, CTAs per SM slot)
 OUT = [None]
 
 
@@ -87,7 +87,7 @@ def ncu_pass(N):
     g = torch.empty(m * m, dtype=torch.float64, device='cuda')
     wsb = lib.rl_gram_ws_bytes(1, m, m, n)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device='cuda')
-    for (mode, il) in ((2, 8),):
+    for (mode, il) in ((3, 8),):
         lib.rl_debug_set_knob(KNOB_GRAM_TMA, mode)
         lib.rl_debug_set_knob(KNOB_GRAM_WAVES, il)
         wsb = lib.rl_gram_ws_bytes(1, m, m, n)
@@ -104,7 +104,7 @@ def ncu_pass(N):
     ip, ix, va = _priv(op, 'indptr'), _priv(op, 'indices'), _priv(op, 'values')
     X, Y = rb.Vectors(n, m), rb.Vectors(n, m)
     X.fill_random_device(3)
-    for group, wps, pf in ((0, 24, 0), (0, 24, 1), (4, 24, 1), (0, 16, 1)):
+    for group, wps, pf in ((0, 24, 1), (0, 24, 3), (0, 24, 7)):
         ob = None
         lib.rl_debug_set_knob(KNOB_SPMM_WPS, wps)
         lib.rl_debug_set_knob(KNOB_SPMM_PF, pf)
@@ -217,15 +217,15 @@ if __name__ == '__main__':
     if 'edge' in only:
         gram_edge_checks()
     if 'gram' in only:
-        gram_sweep(2097152, [(32, 32), (16, 16), (8, 8), (32, 16), (32, 8), (24, 24), (64, 64)], args.reps)
+        gram_sweep(2097152, [(32, 32), (16, 16), (8, 8), (32, 16), (24, 24)], args.reps)
         gram_sweep(140874, [(32, 32)], args.reps)
         gram_sweep(32768, [(16, 16)], args.reps)
     if 'spmm' in only:
         N = args.N
         spmm_sweep('lap3d_%d' % N, lap3d_slab(N, 0, N ** 3),
-                   [(32, (0, 4, 8), ((24, 0), (24, 1), (16, 0), (16, 1))), (16, (0, 4), ((24, 0), (24, 1))), (8, (0,), ((24, 0), (24, 1)))], args.reps)
-        spmm_sweep('lap3d_32', lap3d_slab(32, 0, 32 ** 3), [(16, (0, 4), ((24, 0), (24, 1)))], args.reps)
+                   [(32, (0,), ((24, -1), (24, 1), (24, 3), (24, 7), (24, 5))), (16, (0,), ((24, -1), (24, 1), (24, 3), (24, 7))), (8, (0,), ((24, -1), (24, 1), (24, 3)))], args.reps)
+        spmm_sweep('lap3d_32', lap3d_slab(32, 0, 32 ** 3), [(16, (0,), ((24, -1), (24, 1), (24, 3)))], args.reps)
         from tests_common import spd_c3_like
         offs = tuple(sorted(set([1, 2, 3, 4, 5, 6, 440, 441, 442, 443, 444, 445, 446, 2656, 2657, 2658, 2659, 2660,
                                  2661, 2662, 2214, 2215, 2216, 2217, 3100, 3101, 3102])))
-        spmm_sweep('c3like_55nnz', spd_c3_like(140874, offsets=offs), [(32, (0,), ((24, 0), (24, 1), (16, 0), (16, 1)))], args.reps)
+        spmm_sweep('c3like_55nnz', spd_c3_like(140874, offsets=offs), [(32, (0,), ((16, -1), (16, 1), (16, 3)))], args.reps)
