@@ -389,7 +389,7 @@ def test_matrix_minmax_and_amatrix_scale(gpu_backend, dtype, ref_root):
     for shape in ((1, 2), (3, 1001), (257, 130), (64, 70000)):
         a = (rng.randn(*shape) * 3).astype(dtype)
         a[-1, -1] = -50.0
-        a[0, shape[1] // 2] = 40.0
+        a[0, 0] = 40.0
         for arr in (a, np.asfortranarray(a)):
             lo, hi = gpu_backend.Matrix(arr).minmax()
             assert lo == np.amin(a) == -50.0 and hi == np.amax(a) == 40.0
@@ -434,3 +434,46 @@ def test_spmm_long_rows_csr_batches_and_sell_layout(gpu_backend, dtype):
             X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(3000, m, dtype)
             op.apply(X, Y)
             close(Y.data(), ref, dtype, 100 * float(abs(A).max()))
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_spmm_halo_kernels_on_one_gpu(gpu_backend, dtype):
+    """The row-sharded (halo) variants of the CSR and SELL-32 kernels, driven directly through the
+    C ABI on ONE device: rows [0, nloc) of the operator, owned columns read from the local block,
+    the other columns from a row-interleaved halo buffer built on the host the way the NCCL
+    exchange delivers it (halo[(c - nloc) * m + v])."""
+    from raleigh_b200 import sparse as rsp
+    from raleigh_b200 import device as dev
+    from raleigh_b200._lib import lib, check, dtype_code
+    from tests_common import spd_c3_like
+    offs = (1, 2, 3, 4, 5, 6, 40, 41, 42, 43, 44, 45, 46, 300, 301, 302, 303)
+    A = spd_c3_like(2000, offsets=offs).astype(dtype).tocsr()
+    n, nloc = 2000, 1100
+    slab = A[:nloc].tocsr()
+    slab.sort_indices()
+    halo_cols = np.unique(slab.indices[slab.indices >= nloc])
+    remap = np.arange(n, dtype=np.int64)
+    remap[halo_cols] = nloc + np.arange(halo_cols.size)
+    indptr = np.ascontiguousarray(slab.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(remap[slab.indices], dtype=np.int32)
+    values = np.ascontiguousarray(slab.data, dtype=dtype)
+    d_ip, d_ix, d_va = rsp._to_device(indptr), rsp._to_device(indices), rsp._to_device(values)
+    sell = rsp._build_sell32(indptr, indices, values)
+    assert sell is not None
+    code = dtype_code(dtype)
+    rng = np.random.RandomState(12)
+    for m in (1, 8, 13, 35):
+        x = rng.randn(m, n).astype(dtype)
+        ref = (slab @ x.T).T
+        X = gpu_backend.Vectors(np.ascontiguousarray(x[:, :nloc]))
+        H = rsp._to_device(np.ascontiguousarray(x[:, halo_cols].T))         # (nhalo, m): row-interleaved
+        scale = 100 * float(abs(A).max())
+        Y = gpu_backend.Vectors(nloc, m, dtype)
+        check(lib.rl_csr_spmm_halo(code, nloc, slab.nnz, d_ip.ptr, d_ix.ptr, d_va.ptr, X._wptr(), X._ld, Y._wptr(),
+                                   Y._ld, m, nloc, H.ptr, dev.stream()))
+        close(Y.data(), ref, dtype, scale)
+        Y2 = gpu_backend.Vectors(nloc, m, dtype)
+        sp_, sc_, sv_, nsl = sell
+        check(lib.rl_sell_spmm_halo(code, nloc, slab.nnz, nsl, sp_.ptr, sc_.ptr, sv_.ptr, X._wptr(), X._ld,
+                                    Y2._wptr(), Y2._ld, m, nloc, H.ptr, dev.stream()))
+        close(Y2.data(), ref, dtype, scale)
