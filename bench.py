@@ -430,11 +430,12 @@ def hbm_kernel_rates(peak_gbs):
 def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
-    def timed(fn, reps=5):
+    def timed(fn, reps=5, write_flush=True):
         fn()
         best = []
         for _ in range(reps):
-            flush.zero_()
+            if write_flush:
+                flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             torch.cuda.synchronize()
@@ -454,6 +455,11 @@ def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
     by = 2.0 * n * m * 8
     out['gram'] = {'shape': 'n=%d, m=k=%d, fp64' % (n, m), 'ms': ms, 'GBps': by / ms / 1e6,
                    'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs, 'TFLOPs': 2.0 * n * m * m / ms / 1e9}
+    # second reading without the write flush: the inputs (1.07 GB) exceed L2 (126 MB) on their own, and
+    # the 256 MB memset leaves L2 full of DIRTY lines whose write-back is charged to a read-only kernel
+    ms2 = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
+                                          dev.stream())), write_flush=False)
+    out['gram'].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
     N = 128
 
     def lap1(k):
@@ -466,6 +472,8 @@ def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
     by = nnz * 12.0 + (n + 1) * 8.0 + 2.0 * n * m * 8
     out['spmm'] = {'shape': '7-point Laplacian 128^3 (n=%d, nnz=%d), m=%d, fp64, %s' % (n, nnz, m, A.layout()),
                    'ms': ms, 'GBps': by / ms / 1e6, 'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs}
+    ms2 = timed(lambda: A.apply(X, Y), write_flush=False)
+    out['spmm'].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
     return out
 
 
