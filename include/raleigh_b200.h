@@ -146,8 +146,11 @@ int rl_gram_acc64(int dtype, const void* s, int64_t lds, int64_t m, const void* 
 void rl_debug_set_gram_simt(int on);
 void rl_debug_set_update_fma(int on);
 void rl_debug_set_spmm_warps(int warps);
-/* generic A/B knob (0 = library default): 0 = TMA-fed fp64 Gram (1 on / -1 off, 2 = shallow ring),
- * 1 = SpMM kernel (1 = staged CSR, 2 = SELL-32, 3 = footprint-staged), 2/3 = its vector group / rows per CTA */
+/* generic A/B knobs for measurements (value 0 = library default).  knob 0: fp64 Gram kernel (-1 register
+ * fragments, 1 / 2 TMA ring with one / two CTAs per SM, 3 persistent with dynamic row chunks); 1: SpMM
+ * shared-memory carve-out in percent; 2: SpMM register budget (16 or 24 resident warps per SM); 3: SpMM L2
+ * prefetch mode (-1 off, bit mask); 4: interleaved row steps in the register Gram kernel; 5: Gram CTAs per SM
+ * slot / chunks per CTA.  tools/sweep_r1e.py drives them; results in profiles/r1e_gram_spmm.md. */
 void rl_debug_set_knob(int knob, int value);
 int rl_debug_get_knob(int knob);
 /* Vectors.multiply(q, out) dense_cublas.py:271-299 (gemm, beta=0) and

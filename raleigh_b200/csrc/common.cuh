@@ -10,8 +10,14 @@
 namespace rl {
 
 extern int64_t g_launches;          // kernels launched by this library (api.cu)
-// A/B knobs set through rl_debug_set_knob (api.cu); 0 = library default everywhere
-enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_MODE = 1, KNOB_SPMM_VG = 2, KNOB_SPMM_ROWS = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_COUNT = 16 };
+// A/B knobs set through rl_debug_set_knob (api.cu); 0 = library default everywhere:
+//  GRAM_TMA: -1 register-fragment kernel, 1 / 2 TMA ring with 1 / 2 CTAs per SM, 3 persistent with dynamic
+//            chunks (+4: interleaved stages); GRAM_WAVES: CTAs per SM slot (modes 1, 2) / chunks per CTA (3);
+//  GRAM_INTERLEAVE: interleaved row steps in the register-fragment kernel;
+//  SPMM_CARVEOUT: shared-memory carve-out in percent; SPMM_WPS: 16 = 127-register budget + 4-entry batches,
+//            24 = 80 registers + 2-entry batches; SPMM_PREFETCH: -1 off, bit 0 largest-column lines,
+//            bit 1 CSR entries of the run one resident window ahead, bit 2 X lines shifted by that window
+enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_COUNT = 16 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 

@@ -11,21 +11,19 @@
 // memory ONCE with coalesced loads and re-reads them from there for every group
 // of VG vectors, so the matrix is streamed from HBM exactly once per SpMM no
 // matter how many vectors the block has.  The X gathers go through L1/L2: the
-// reuse distance of a stencil (one grid plane) is L2-resident.
+// reuse distance of a stencil (one grid plane) is L2-resident; what they wait for
+// is lines still in flight from DRAM, hence the L2 prefetch below.
+// Measurements and ncu readings behind every choice here: profiles/r1e_gram_spmm.md.
 #include "common.cuh"
 
 namespace rl {
 
-// Warps per CTA.  Consecutive rows share gathered lines (stencil neighbours at +-1, +-N):
-// the more consecutive rows a CTA covers, the more of those gathers hit L1 instead of L2.
-// Measured on B200 (profiles/r1c_kernel_tuning.md).
 #ifndef RL_SPMM_PF_DEFAULT
 #define RL_SPMM_PF_DEFAULT 1      // bit 0 measured: 0.381 -> 0.330 ms on the 128^3 Laplacian (m = 32)
 #endif
-#ifndef RL_SPMM_WPS_DEFAULT
-#define RL_SPMM_WPS_DEFAULT 24
-#endif
-static int g_spmm_warps = 4;     // 16-warp CTAs measured slower (2.2 vs 3.2 TB/s on 128^3 and 256^3 Laplacians): their staging buffers shrink L1
+// Warps (32-row runs) per CTA: 4.  8- and 16-warp CTAs were slower with consecutive runs (r1c) and with
+// footprint-clustered runs (r1e: 0.3625 / 0.381 / 0.479 ms for 4 / 8 / 16).
+static int g_spmm_warps = 4;
 
 // Column c of the operator: owned columns come from the local block X (vector-major),
 // halo columns (c >= ncols_local, row-sharded operator) from the exchanged halo buffer H,
@@ -233,15 +231,15 @@ static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indi
     }
     // A/B knob: shared-memory carve-out in percent (the rest of the 256 KB is L1 for the X gathers)
     static int carveout = 0;
-    if (g_knob[KNOB_SPMM_MODE] != carveout) {
-        carveout = g_knob[KNOB_SPMM_MODE];
+    if (g_knob[KNOB_SPMM_CARVEOUT] != carveout) {
+        carveout = g_knob[KNOB_SPMM_CARVEOUT];
         RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      carveout > 0 ? carveout : cudaSharedmemCarveoutDefault));
     }
     int64_t blocks = (nrows + W * 32 - 1) / (W * 32);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(nrows, indptr, indices, values, x, ldx, y, ldy, m, cap, ncols_local,
                                                  halo, run_order,
-                                                 g_knob[KNOB_SPMM_ROWS] > 0 ? g_knob[KNOB_SPMM_ROWS] : (g_knob[KNOB_SPMM_ROWS] < 0 ? 0 : RL_SPMM_PF_DEFAULT),
+                                                 g_knob[KNOB_SPMM_PREFETCH] > 0 ? g_knob[KNOB_SPMM_PREFETCH] : (g_knob[KNOB_SPMM_PREFETCH] < 0 ? 0 : RL_SPMM_PF_DEFAULT),
                                                  sm_count() * WPS);
     return check_launch();
 }
@@ -260,7 +258,7 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     if (warps >= 8 && (size_t)warps * cap * (sizeof(T) + 4) > 96 * 1024) warps = 4;
     // long rows (>= 16 entries on average): four entries x 8 vectors in flight per lane and the
     // 127-register budget win (55 nnz/row: 0.24 -> 0.16 ms); stencils keep 24 warps per SM
-    const bool fat = g_knob[KNOB_SPMM_VG] == 16 || (g_knob[KNOB_SPMM_VG] == 0 && nnz >= 16 * nrows);
+    const bool fat = g_knob[KNOB_SPMM_WPS] == 16 || (g_knob[KNOB_SPMM_WPS] == 0 && nnz >= 16 * nrows);
 #define RL_SPMM_ARGS nrows, indptr, indices, (const T*)values, (const T*)x, ldx, (T*)y, ldy, (int)m, cap, ncols_local
 #define RL_SPMM_W(W_) do { \
         if (halo) return spmm_launch<T, W_, true, 24, 2>(RL_SPMM_ARGS, (const T*)halo, run_order, st); \
