@@ -177,6 +177,21 @@ class _DenseMatrixNumpyProxy:
         return r[1]
 
 
+def _big_lapack_threads():
+    """Threads a big LAPACK call may use: at most 4, and never more than this process's share of the
+    cores it may run on -- one process per GPU means up to 8 of them factorise at the same moment, and
+    an oversubscribed OpenBLAS is catastrophically slow (measured: 16 threads on 8 cores, 0.3 s -> 10 s)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    try:
+        procs = int(os.environ.get('LOCAL_WORLD_SIZE') or os.environ.get('WORLD_SIZE') or 1)
+    except ValueError:
+        procs = 1
+    return max(1, min(4, cores // max(1, procs)))
+
+
 def shim_host_hotspots():
     """`solver._norm` (solver.py:1745-1746) is `numpy.apply_along_axis(numpy.linalg.norm, ...)`:
     one Python-level call per column, called for every pivot of `_piv_chol` (solver.py:1765-1768)
@@ -199,7 +214,7 @@ def shim_host_hotspots():
     try:
         import threadpoolctl  # noqa: F401
         import raleigh.interfaces.partial_svd as psvd
-        threads = int(os.environ.get('RALEIGH_B200_BIG_LAPACK_THREADS', min(4, os.cpu_count() or 1)))
+        threads = int(os.environ.get('RALEIGH_B200_BIG_LAPACK_THREADS', _big_lapack_threads()))
         if not isinstance(psvd.sla, _BigLapackProxy):
             psvd._reference_sla = psvd.sla
             psvd.sla = _BigLapackProxy(psvd.sla, threads)

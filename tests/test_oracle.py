@@ -284,3 +284,28 @@ def test_host_hotspot_shim_matches_reference_norm_and_piv_chol(ref_root):
     finally:
         compat.unshim_host_hotspots()
     assert not isinstance(psvd.sla, compat._BigLapackProxy)
+
+
+def test_host_shims_do_not_change_solver_iterations_or_eigenvalues(ref_root):
+    """The golden solver runs (reference core solver on the oracle backend) repeated with
+    compat.shim_host_hotspots() active: same iteration counts, eigenvalues equal to the golden
+    ones -- the vectorised `_norm` may differ in the last bit but never changes a decision here."""
+    from raleigh_b200 import compat
+    rs = _ref_solver(ref_root)
+    g = np.load(os.path.join(GOLDEN, 'solver.npz'))
+    assert compat.shim_host_hotspots()
+    try:
+        assert rs._norm is compat._column_norms
+        a = np.arange(1, 101).astype(np.float64)
+        st, it, lmd, _ = run_solver(rs, oracle.Vectors, oracle.Matrix(np.diag(a)), 100, np.float64, (6, 0), 1e-8, -1,
+                                    crit='eigenvector error', max_iter=-1)
+        assert it == int(g['diag_iter']) == 58
+        assert np.allclose(lmd, [1, 2, 3, 4, 5, 6], atol=1e-10)
+        L = K.lap3d_csr(12, 12, 12)
+        st, it, lmd, _ = run_solver(rs, oracle.Vectors, oracle.SparseSymmetricMatrix(L), L.shape[0], np.float64,
+                                    (6, 0), 1e-6, 8)
+        assert st == 0 and it == int(g['lap_iter'])
+        assert np.max(np.abs(lmd - g['lap_lmd']) / g['lap_lmd']) < 1e-10
+    finally:
+        compat.unshim_host_hotspots()
+    assert rs._norm is not compat._column_norms
