@@ -28,6 +28,7 @@ from microbench import timeit, peak_gbs  # noqa: E402
 from run_c4 import lap3d_slab  # noqa: E402
 
 KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_SPMM_PF, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 3, 4, 5
+KNOB_SPMM_WINDOW, KNOB_SPMM_WIN_CHUNKS = 6, 7
 GRAM_MODES = [(-1, 0), (0, 0), (3, 4), (3, 8), (3, 16), (3, 32)]      # (TMA mode, CTAs per SM slot)
 OUT = [None]
 
@@ -195,6 +196,22 @@ def spmm_sweep(name, A_full, plans, reps):
                  sq_diff_vs_default=diff)
       lib.rl_debug_set_knob(KNOB_SPMM_WPS, 0)
       lib.rl_debug_set_knob(KNOB_SPMM_PF, 0)
+      if '--window' in sys.argv:            # experimental band-window kernel (spmm_win.cu), checked against the default
+          for chunks in (1, 4, 8):
+              lib.rl_debug_set_knob(KNOB_SPMM_WINDOW, 1)
+              lib.rl_debug_set_knob(KNOB_SPMM_WIN_CHUNKS, chunks)
+              f = lambda: check(lib.rl_csr_spmm_ex(1, n, nnz, ip.ptr, ix.ptr, va.ptr, X._wptr(), X._ld, Y._wptr(), Y._ld, m,
+                                                   0, None, None, 4, dev.stream()))
+              Y.zero()
+              f()
+              torch.cuda.synchronize()
+              check(lib.rl_axpy(1, Y._wptr(), Y._ld, Y0._wptr(), Y0._ld, m, n, -1.0, dev.stream()))
+              diff = float(np.abs(Y.dots(Y)).max())
+              ms, best = timeit(f, reps=reps)
+              emit(exp='spmm_window', matrix=name, n=n, nnz=nnz, m=m, chunks=chunks, ms=round(ms, 5), ms_best=round(best, 5),
+                   GBps=round(byts / ms / 1e6, 1), frac_hbm=round(byts / ms / 1e6 / peak_gbs(), 3), sq_diff_vs_default=diff)
+          lib.rl_debug_set_knob(KNOB_SPMM_WINDOW, 0)
+          lib.rl_debug_set_knob(KNOB_SPMM_WIN_CHUNKS, 0)
       if op.layout() == 'sell32':
         ms, best = timeit(lambda: op.apply(X, Y), reps=reps)
         emit(exp='spmm', matrix=name, n=n, nnz=nnz, m=m, group='sell32', ms=round(ms, 5), GBps=round(byts / ms / 1e6, 1),
@@ -208,6 +225,7 @@ if __name__ == '__main__':
     ap.add_argument('--N', type=int, default=128)
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--only', default='edge,gram,spmm')
+    ap.add_argument('--window', action='store_true', help='also time the experimental band-window SpMM kernel')
     args = ap.parse_args()
     only = set(args.only.split(','))
     if args.out:
