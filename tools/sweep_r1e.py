@@ -4,7 +4,15 @@ Every variant is first checked against the default kernel on the same inputs (Gr
 difference of the k x m result; SpMM: Y must be bit-identical, the per-row arithmetic does not
 change), then timed with CUDA events, L2 flushed between repetitions.
 
-    python tools/sweep_r1e.py [--out gpurun_out/sweep_r1e.jsonl] [--N 128]
+    python tools/sweep_r1e.py [--out gpurun_out/sweep_r1e.jsonl] [--N 128] [--only edge,gram,spmm] [--window]
+
+ncu captures of the variants (one launch each; `gram_reduce` included so that the C-ABI call can be
+split into its two kernels):
+
+    ncu --set full --clock-control none --import-source on \
+        -k regex:"gram_tma|gram_dmma|gram_reduce|spmm_kernel|spmm_win" -o gpurun_out/prof -f \
+        python tools/sweep_r1e.py --only ncu
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --title "..." > profiles/xxx.md
 """
 import argparse
 import ctypes
