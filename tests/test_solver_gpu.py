@@ -129,3 +129,22 @@ def test_pca_doctest(gpu_backend, ref):
     em, ef = pca_error(A, mean, trans, comps)
     assert '%.0e %.0e' % (em, ef) == '2e-02 4e-02'
     assert abs(comps.shape[0] - int(g['doc_tol_ncomp'])) <= 5
+
+
+@pytest.mark.skipif(os.environ.get('RALEIGH_B200_LONG_TESTS', '0') != '1',
+                    reason='written after the round-1 GPU budget was spent: first run is manual (RALEIGH_B200_LONG_TESTS=1)')
+@pytest.mark.parametrize('block', [8, 16])
+def test_laplacian_fp64_large_enough_for_the_tma_gram(gpu_backend, ref, block):
+    """n = 24^3 = 13,824 >= 8192: every Vectors.dot of the solve goes through the TMA-fed Gram kernel
+    (all tile shapes as windows shrink) and the SpMM runs with the L2 prefetch; eigenvalues against
+    the analytic spectrum of the 7-point Laplacian, residuals below the solver tolerance."""
+    L = K.lap3d_csr(24, 24, 24)
+    n = L.shape[0]
+    op = gpu_backend.SparseSymmetricMatrix(L)
+    st, it, lmd, v = _solve(ref, gpu_backend.Vectors, op, n, np.float64, (6, 0), 1e-6, block)
+    assert st == 0
+    exact = K.lap3d_eigenvalues(24, 24, 24)[:6]
+    assert np.max(np.abs(np.sort(lmd) - exact) / exact) < 1e-10, (it, lmd)
+    x = v.data()
+    res = np.linalg.norm(L @ x.T - x.T * lmd[None, :], axis=0)
+    assert np.max(res / lmd) < 1e-5
