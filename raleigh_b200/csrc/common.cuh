@@ -17,8 +17,9 @@ extern int64_t g_launches;          // kernels launched by this library (api.cu)
 //  SPMM_CARVEOUT: shared-memory carve-out in percent; SPMM_WPS: 16 = 127-register budget + 4-entry batches,
 //            24 = 80 registers + 2-entry batches; SPMM_PREFETCH: -1 off, bit 0 largest-column lines,
 //            bit 1 CSR entries of the run one resident window ahead, bit 2 X lines shifted by that window;
-//  SPMM_WINDOW: 1 = experimental band-window kernel (spmm_win.cu), SPMM_WIN_CHUNKS: its CTAs per SM slot
-enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_SPMM_WINDOW = 6, KNOB_SPMM_WIN_CHUNKS = 7,
+//  SPMM_WINDOW: 1 = experimental band-window kernel (spmm_win.cu), SPMM_WIN_CHUNKS: its CTAs per SM slot;
+//  GEMM_INSPLIT: 1 = experimental in-kernel lo split of the tcgen05 dense apply (gemm_tc.cu)
+enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_SPMM_WINDOW = 6, KNOB_SPMM_WIN_CHUNKS = 7, KNOB_GEMM_INSPLIT = 8,
             KNOB_COUNT = 16 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount

@@ -93,7 +93,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// INSPLIT (EXPERIMENTAL, knob 8, unmeasured): only the raw fp32 tiles of X and A are loaded; four extra
+// warps compute the low parts (a - tf32_trunc(a), elementwise, hence layout-agnostic) from shared memory
+// into the Xlo / Alo slots of the stage and hand the stage to the MMA issuer through ready[].  Halves
+// the HBM traffic (no materialised lo copy of the data matrix) and the L2->SM traffic of the kernel.
+template <bool INSPLIT>
+__global__ void __launch_bounds__(INSPLIT ? TC_THREADS + 128 : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                const TcParams p) {
@@ -104,7 +109,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     uint64_t* empty = bars + TC_STAGES;            // [TC_STAGES]
     uint64_t* tfull = bars + 2 * TC_STAGES;        // [2]
     uint64_t* tempty = bars + 2 * TC_STAGES + 2;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* ready = bars + 2 * TC_STAGES + 4;    // [TC_STAGES] (INSPLIT: lo tiles written)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int units = p.vblocks * p.tiles * p.splits;
@@ -112,6 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&ready[s], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -134,17 +141,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = smem + stage * TC_STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], INSPLIT ? 2 * TC_TILE_BYTES : TC_STAGE_BYTES);
                     tma_load_2d(st, &tm_xhi, &full[stage], kb * TC_BK, vb * TC_BM);
-                    tma_load_2d(st + TC_TILE_BYTES, &tm_xlo, &full[stage], kb * TC_BK, vb * TC_BM);
+                    if (!INSPLIT) tma_load_2d(st + TC_TILE_BYTES, &tm_xlo, &full[stage], kb * TC_BK, vb * TC_BM);
                     if (!p.transp) {
                         tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_ahi, &full[stage], kb * TC_BK, tile * TC_BN);
-                        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_alo, &full[stage], kb * TC_BK, tile * TC_BN);
+                        if (!INSPLIT) tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_alo, &full[stage], kb * TC_BK, tile * TC_BN);
                     } else {
 #pragma unroll
                         for (int c = 0; c < TC_BN / 32; ++c) {
                             tma_load_2d(st + 2 * TC_TILE_BYTES + c * 4096, &tm_ahi, &full[stage], tile * TC_BN + c * 32, kb * TC_BK);
-                            tma_load_2d(st + 3 * TC_TILE_BYTES + c * 4096, &tm_alo, &full[stage], tile * TC_BN + c * 32, kb * TC_BK);
+                            if (!INSPLIT) tma_load_2d(st + 3 * TC_TILE_BYTES + c * 4096, &tm_alo, &full[stage], tile * TC_BN + c * 32, kb * TC_BK);
                         }
                     }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -167,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * TC_BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(INSPLIT ? &ready[stage] : &full[stage], phase);
                     tc_fence_after();
                     const uint32_t sx_hi = smem_u32(smem + stage * TC_STAGE_BYTES);
                     const uint32_t sx_lo = sx_hi + TC_TILE_BYTES;
@@ -195,6 +202,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[as]);                   // accumulator complete
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== INSPLIT only: low-part warps (6..9) =====
+        // same (unit, k-block) walk as the producer; each stage: wait for the raw tiles, write
+        // lo = a - tf32_trunc(a) of the X and A tiles into the slots behind them (same offsets, so the
+        // swizzled layout carries over), make the writes visible to the async proxy, hand over
+        uint8_t* smem_s = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+        const int tid = threadIdx.x - TC_THREADS;
+        int stage = 0; uint32_t phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int split = u % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                uint8_t* st = smem_s + stage * TC_STAGE_BYTES;
+#pragma unroll
+                for (int tsel = 0; tsel < 2; ++tsel) {
+                    const float4* src = reinterpret_cast<const float4*>(st + 2 * tsel * TC_TILE_BYTES);
+                    float4* dst = reinterpret_cast<float4*>(st + (2 * tsel + 1) * TC_TILE_BYTES);
+#pragma unroll
+                    for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
+                        const float4 a = src[tid + i * 128];
+                        float4 o;
+                        o.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+                        o.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+                        o.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+                        o.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+                        dst[tid + i * 128] = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -328,22 +371,25 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx) {
     return tma_encode_fn() != nullptr && host_aligned16(a) && host_aligned16(x) && (lda % 4 == 0) && (ldx % 4 == 0);
 }
 
-int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_t N, const float* x, int64_t ldx,
+int gemm_tc(const float* a_hi, const float* a_lo_in, int64_t lda, int64_t M, int64_t N, const float* x, int64_t ldx,
             float* y, int64_t ldy, int64_t k, int transp, double alpha, double beta, void* ws, size_t ws_bytes,
             cudaStream_t st) {
     TcPlan pl = tc_plan(M, N, k, transp);
     if (ws_bytes < pl.ws_bytes) return RL_E_WORKSPACE;
+    const float* a_lo = a_lo_in;
     const int64_t nout = transp ? N : M, kred = transp ? M : N;
     float* x_lo = reinterpret_cast<float*>(ws);
-    {
+    const bool insplit = g_knob[KNOB_GEMM_INSPLIT] == 1;      // experimental: lo parts computed in shared memory
+    if (!insplit) {
         dim3 g((unsigned)((kred / 4 + 256) / 256), (unsigned)(k < 65535 ? k : 65535));
         split_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, x_lo, pl.ld_xlo, k, kred);
         int rc = check_launch();
         if (rc) return rc;
     }
     CUtensorMap mxh, mxl, mah, mal;
+    if (insplit) { x_lo = const_cast<float*>(x); a_lo = a_hi; }     // the lo maps are encoded but never used
     int rc = make_map(&mxh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, kred, k, ldx, TC_BK, TC_BM);
-    if (!rc) rc = make_map(&mxl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x_lo, kred, k, pl.ld_xlo, TC_BK, TC_BM);
+    if (!rc) rc = make_map(&mxl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x_lo, kred, k, insplit ? ldx : pl.ld_xlo, TC_BK, TC_BM);
     if (!transp) {
         if (!rc) rc = make_map(&mah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_hi, N, M, lda, TC_BK, TC_BN);
         if (!rc) rc = make_map(&mal, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_lo, N, M, lda, TC_BK, TC_BN);
@@ -359,12 +405,14 @@ int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_
     p.kb_per_split = pl.kb_per_split; p.transp = transp ? 1 : 0; p.alpha = (float)alpha; p.beta = (float)beta;
     static bool configured = false;
     if (!configured) {
-        RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         configured = true;
     }
     const int units = pl.tiles * pl.vblocks * pl.splits;
     const int grid = units < sm_count() ? units : sm_count();
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(mxh, mxl, mah, mal, p);
+    if (insplit) gemm_tc_kernel<true><<<grid, TC_THREADS + 128, TC_SMEM, st>>>(mxh, mxl, mah, mal, p);
+    else gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(mxh, mxl, mah, mal, p);
     rc = check_launch();
     if (rc) return rc;
     if (pl.splits > 1) {

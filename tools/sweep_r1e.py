@@ -124,6 +124,32 @@ def ncu_pass(N):
     torch.cuda.synchronize()
 
 
+def gemm_sweep(M, N, k, reps):
+    """tcgen05 dense apply: default (lo copies streamed from HBM) vs the experimental in-kernel lo split
+    (knob 8), both orientations; the split variant must reproduce the default to fp32 rounding."""
+    KNOB_GEMM_INSPLIT = 8
+    a = torch.randn(M, N, dtype=torch.float32, device='cuda').cpu().numpy()
+    A = rb.Matrix(a)
+    x, y = rb.Vectors(N, k, np.float32), rb.Vectors(M, k, np.float32)
+    x.fill_random_device(4)
+    y2, x2 = rb.Vectors(M, k, np.float32), rb.Vectors(N, k, np.float32)
+    fl = 2.0 * M * N * k
+    for transp in (False, True):
+        src, dst, dst2 = (y, x, x2) if transp else (x, y, y2)
+        lib.rl_debug_set_knob(KNOB_GEMM_INSPLIT, 0)
+        A.apply(src, dst, transp=transp)
+        ms0, _ = timeit(lambda: A.apply(src, dst, transp=transp), reps=reps, warm=1)
+        lib.rl_debug_set_knob(KNOB_GEMM_INSPLIT, 1)
+        A.apply(src, dst2, transp=transp)
+        ms1, _ = timeit(lambda: A.apply(src, dst2, transp=transp), reps=reps, warm=1)
+        lib.rl_debug_set_knob(KNOB_GEMM_INSPLIT, 0)
+        d0, d1 = dst.data(), dst2.data()
+        err = float(np.abs(d0 - d1).max() / np.abs(d0).max())
+        emit(exp='gemm_insplit', shape='A=%dx%d,k=%d' % (M, N, k), transp=transp, ms_default=round(ms0, 4),
+             ms_insplit=round(ms1, 4), TFLOPs_default=round(fl / ms0 / 1e9, 1), TFLOPs_insplit=round(fl / ms1 / 1e9, 1),
+             max_rel_diff=err, ok=bool(err < 1e-5))
+
+
 def gram_edge_checks():
     """Ragged n, windows with an offset, m != k, against float64 NumPy on the host."""
     rng = np.random.RandomState(5)
@@ -246,6 +272,10 @@ if __name__ == '__main__':
         gram_sweep(2097152, [(32, 32), (16, 16), (8, 8), (32, 16), (24, 24)], args.reps)
         gram_sweep(140874, [(32, 32)], args.reps)
         gram_sweep(32768, [(16, 16)], args.reps)
+    if 'gemm' in only:
+        gemm_sweep(12000, 39375, 128, 5)
+        gemm_sweep(3000, 2000, 128, 5)
+        gemm_sweep(1000, 777, 40, 3)
     if 'spmm' in only:
         N = args.N
         spmm_sweep('lap3d_%d' % N, lap3d_slab(N, 0, N ** 3),
