@@ -258,6 +258,81 @@ size_t rl_syevj_ws_bytes(int64_t p);
 int rl_syevj(double* a, int64_t p, double* w, void* ws, size_t ws_bytes,
              int* sweeps_out_h, void* stream);
 
+
+/* ---- device-resident Rayleigh-Ritz (no host LAPACK) ------------
+ * Small matrices are fp64, row-major with a leading dimension, and live in device memory for
+ * the whole solve; nothing below synchronises.  The reference does all of this on the host
+ * with NumPy / SciPy between two block-vector operations (raleigh/core/solver.py:838-1663). */
+/* Vectors.dot without the D2H copy (dense_cublas.py:245-269): out[i*ldout + j] = <o_i, s_j>,
+ * fp64 whatever the data type (fp32 data accumulate in fp64) */
+int rl_gram_dev(int dtype, const void* s, int64_t lds, int64_t m, const void* o, int64_t ldo,
+                int64_t k, int64_t n, double* out, int64_t ldout, void* stream);
+/* Vectors.dots into a device fp64 vector (dense_cublas.py:222-243) */
+int rl_dots_dev(int dtype, const void* s, int64_t lds, const void* o, int64_t ldo, int64_t m,
+                int64_t n, double* out, void* stream);
+/* Vectors.multiply / add(other, s, q) with device-resident fp64 coefficients q (k x m, ldq)
+ * (dense_cublas.py:271-342 without the H2D copy): Out = beta Out + alpha q^T X */
+int rl_update_dev(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64_t ldx,
+                  int64_t k, const double* q, int64_t ldq, double alpha, double beta, int64_t n,
+                  void* stream);
+/* residuals W[j] = AX[j] - lmd[j] X[j] (solver.py:946-952: copy + per-vector axpy), lmd on the device */
+int rl_residual_dev(int dtype, void* w, int64_t ldw, const void* ax, int64_t ldax, const void* x,
+                    int64_t ldx, int64_t m, int64_t n, const double* lmd, void* stream);
+/* Y[j] /= sqrt(|s2[j]|) unless zero (solver.py:1377-1378: sqrt on the host + Vectors.scale) */
+int rl_scale_rsqrt_dev(int dtype, void* y, int64_t ldy, int64_t m, int64_t n, const double* s2,
+                       void* stream);
+/* small-matrix utilities: dst = src; dst = src^T; G[nx+j][i] = G[i][nx+j]; C = alpha op(A) op(B) + beta C */
+int rl_small_copy(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows,
+                  int64_t cols, void* stream);
+int rl_small_transpose(const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows,
+                       int64_t cols, void* stream);
+int rl_small_mirror(double* g, int64_t ld, int64_t nx, int64_t ny, void* stream);
+int rl_small_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
+                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                  int64_t ldc, void* stream);
+/* mode 0: solve U^T X = B, mode 1: solve U X = B; U upper triangular n x n, B n x r overwritten
+ * (scipy.linalg.solve_triangular at solver.py:1592, 1686-1687) */
+int rl_small_trsm(int mode, const double* U, int64_t ldu, int64_t n, double* B, int64_t ldb,
+                  int64_t r, void* stream);
+/* Rayleigh quotients and restart indicators (solver.py:859-873): lmd[i] = xax[i][i] / xbx[i][i],
+ * stats[0] = max|lmd - lmdx| / max|lmdx|, stats[1] = max|xbx - I| */
+int rl_rr_ritz_check(const double* xax, const double* xbx, int64_t ld, int64_t nx,
+                     const double* lmdx, double* lmd, double* stats, void* stream);
+/* conjugation coefficients (solver.py:1331-1347): beta = num / den unless |num| >= 100 s |den| */
+int rl_rr_conjugation(const double* zay, const double* zby, double* beta, int64_t ld, int64_t nz,
+                      int64_t ny, const double* lmd, const double* lmdz, const double* sy2,
+                      const double* sz2, void* stream);
+/* _piv_chol (solver.py:1749-1845): in-place upper Cholesky factor of the leading n x n block,
+ * first k columns unpivoted, max-diagonal pivoting and the reference's drop rule on the rest.
+ * a0: scratch of the same shape; ind: n ints (permutation); info: 4 ints (dropped, status,
+ * drop case, last condition check) -- all device memory. */
+int rl_rr_piv_chol(double* a, double* a0, int64_t ld, int64_t n, int64_t k, double eps, int* ind,
+                   int* info, void* stream);
+/* change estimates (solver.py:1475-1493) and coefficient blocks (solver.py:1593-1607) */
+int rl_rr_estimates(const double* q, int64_t ldq, const double* w, int64_t nx, int64_t ny,
+                    int64_t leftX, int64_t rightX, double* dX, double* dlmd, void* stream);
+int rl_rr_select(const double* q, int64_t ldq, const double* w, int64_t nxy, int64_t leftXn,
+                 int64_t rightXn, double* cx, int64_t ldcx, double* cz, int64_t ldcz, double* lmdx,
+                 double* lmdz, void* stream);
+/* scipy.linalg.eigh (solver.py:1459, 1470) on the device.  n <= rl_syevj_cluster_max_n():
+ * one-sided Jacobi on a thread-block cluster, columns in distributed shared memory
+ * (csrc/jacobi.cu); larger: the cooperative-grid kernel behind rl_syevj.  w ascending,
+ * q[i*ldq + j] = component i of eigenvector j; g is read only (both triangles, averaged). */
+int rl_syevj_cluster_max_n(void);
+size_t rl_syevj_cluster_ws_bytes(int64_t n);
+int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq,
+                     void* ws, size_t ws_bytes, int* info_d, void* stream);
+size_t rl_small_eigh_ws_bytes(int64_t n);
+int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq,
+                  void* ws, size_t ws_bytes, int* info_d, void* stream);
+/* the whole Rayleigh-Ritz step (solver.py:1456-1493, 1589-1607): transform, pre-rotation, eigh,
+ * estimates, back-transformation, coefficient blocks.  est: dX at est[0..nx), dlmd at est[nmax..) */
+size_t rl_rr_solve_ws_bytes(int64_t nmax);
+int rl_rr_solve(const double* ga, const double* u, int64_t ld, int64_t nx, int64_t ny,
+                int64_t leftX, int64_t rightX, int64_t leftXn, int64_t rightXn, double* cx,
+                int64_t ldcx, double* cz, int64_t ldcz, double* lmdx, double* lmdz, double* est,
+                int64_t nmax, void* ws, size_t ws_bytes, int* info_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

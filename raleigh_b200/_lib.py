@@ -88,6 +88,31 @@ PROTOTYPES = {
                                  c_vp]),
     'rl_sell_spmm_halo': (c_int, [c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64,
                                   c_vp, c_vp]),
+    'rl_gram_dev': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    'rl_dots_dev': (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    'rl_update_dev': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_i64,
+                              c_vp]),
+    'rl_residual_dev': (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    'rl_scale_rsqrt_dev': (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    'rl_small_copy': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'rl_small_transpose': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'rl_small_mirror': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp]),
+    'rl_small_gemm': (c_int, [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,
+                              c_i64, c_vp]),
+    'rl_small_trsm': (c_int, [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    'rl_rr_ritz_check': (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'rl_rr_conjugation': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'rl_rr_piv_chol': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_dbl, c_vp, c_vp, c_vp]),
+    'rl_rr_estimates': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'rl_rr_select': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    'rl_syevj_cluster_max_n': (c_int, []),
+    'rl_syevj_cluster_ws_bytes': (c_sz, [c_i64]),
+    'rl_syevj_cluster': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    'rl_small_eigh_ws_bytes': (c_sz, [c_i64]),
+    'rl_small_eigh': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    'rl_rr_solve_ws_bytes': (c_sz, [c_i64]),
+    'rl_rr_solve': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
+                            c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
     'rl_syevj_ws_bytes': (c_sz, [c_i64]),
     'rl_syevj': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, ctypes.POINTER(c_int), c_vp]),
 }

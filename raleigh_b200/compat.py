@@ -245,6 +245,37 @@ def unshim_host_hotspots():
         pass
 
 
+DEVICE_SOLVER = os.environ.get('RALEIGH_B200_DEVICE_SOLVER', '1') != '0'
+
+
+def use_device_solver(on=True):
+    """Switch between the device-resident block-CG driver (jcg.py, default) and the reference's own
+    main loop running verbatim on this backend (kept for parity checks)."""
+    global DEVICE_SOLVER
+    DEVICE_SOLVER = bool(on)
+
+
+def hook_device_solver():
+    """Route `Solver._solve` (solver.py:587) to the device-resident driver whenever the problem is one
+    it supports (standard problem on raleigh_b200 vectors); everything else, and everything when
+    DEVICE_SOLVER is off, goes to the reference's own `_solve`.  `Solver.solve` -- argument checks,
+    block size choice, the final dense Rayleigh-Ritz fallback -- stays the reference's."""
+    import raleigh.core.solver as rsolver
+    if getattr(rsolver.Solver, '_reference_solve', None) is not None:
+        return
+    rsolver.Solver._reference_solve = rsolver.Solver._solve
+
+    def _solve(self, eigenvectors, options, which, extra, init):
+        if DEVICE_SOLVER:
+            from . import jcg
+            if jcg.supported(self, eigenvectors):
+                from .engine import DeviceEngine
+                return jcg.solve(self, eigenvectors, options, which, extra, init, DeviceEngine())
+        return self._reference_solve(eigenvectors, options, which, extra, init)
+
+    rsolver.Solver._solve = _solve
+
+
 def install(reference_path=None, sparse=True, dense=True):
     """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.
     Raises ImportError if the reference package cannot be found."""
@@ -272,4 +303,5 @@ def install(reference_path=None, sparse=True, dense=True):
         setattr(algebra, name, mod)
     shim_scipy()
     shim_host_hotspots()
+    hook_device_solver()
     return raleigh

@@ -1,0 +1,482 @@
+"""Device-resident block Jacobi-conjugated-gradient driver.
+
+The reference's main loop (raleigh/core/solver.py:838-1663) alternates a dozen
+block-vector operations with O(m^3) host LAPACK on 2m x 2m matrices -- pivoted
+Cholesky (`_piv_chol`, :1749-1826), two triangular transforms (`_transform`,
+:1685-1688), two symmetric eigenproblems (:1459, :1470) -- and pulls every Gram
+matrix back to the host to feed them (about 14 synchronous round trips per
+iteration).  With the algebra on a B200 that host work IS the run time.
+
+Here the same iteration (Appendix B of SURVEY.md) keeps every Gram matrix and
+every coefficient matrix in device memory:
+
+  * Gram products write fp64 results straight into device-resident small
+    matrices (rl_gram_dev), block updates read their coefficients from there
+    (rl_update_dev);
+  * the pivoted Cholesky factorisation with the reference's drop rule, the
+    conjugation coefficients, the Rayleigh-Ritz reduction, both symmetric
+    eigenproblems and the back-transformation are hand-written kernels
+    (csrc/rr.cu, csrc/jacobi.cu) -- no host LAPACK anywhere;
+  * the host sees three small packets per iteration (Ritz values + residual
+    norms; the number of dropped search directions; the change estimates) and
+    does the convergence bookkeeping on length-m arrays (jcg_host.py);
+  * the block buffers are rotated instead of copied: the reference moves every
+    updated block through the W workspace and copies it back (:1610-1656).
+
+Supported: standard problems A x = lambda x, optional preconditioner, optional
+previously computed eigenvectors, real float32/float64.  Anything else
+(generalised problems) is handed to the reference's own `_solve`.
+
+The driver talks to an `engine` (engine.py: DeviceEngine, ctypes over the C
+ABI).  The tests substitute a NumPy engine to check the control flow against
+the reference solver on the CPU; the product path never does.
+"""
+import math
+
+import numpy
+
+from .jcg_host import BlockLayout, History, initial_split, next_layout
+
+
+class _Fatal(Exception):
+    pass
+
+
+def supported(solver, eigenvectors):
+    """True when the device-resident driver can run this problem."""
+    problem = solver.problem()
+    if problem.type() != 's':
+        return False
+    return hasattr(eigenvectors, '_rl_device_block')
+
+
+def _parse_which(which):
+    try:
+        if len(which) != 2:
+            raise ValueError('which must be either integer or tuple of 2 integers')
+        return False, int(which[0]), int(which[1])
+    except TypeError:
+        return True, which, which
+
+
+class _Pool:
+    """Block buffers of the iteration; roles are rotated instead of copying."""
+
+    def __init__(self, engine, count):
+        self._free = [engine.new_block() for _ in range(count)]
+
+    def take(self, nv):
+        blk = self._free.pop()
+        blk.select(nv)
+        return blk
+
+    def give(self, *blocks):
+        for b in blocks:
+            if b is not None:
+                self._free.append(b)
+
+
+def solve(solver, eigenvectors, options, which, extra, init, engine):
+    """Drop-in for Solver._solve (solver.py:587-1665): same arguments, same
+    attributes set on `solver`, same return codes."""
+    verb = options.verbosity
+    sigma = options.sigma
+    largest, left, right = _parse_which(which)
+    m = solver.block_size
+    left_ratio, left_block = initial_split(m, left, right, largest)
+    lay = BlockLayout(m, left_block)
+
+    extra_left, extra_right = int(extra[0]), int(extra[1])
+    left_total = right_total = 0
+    if left >= 0:
+        left_total = left + extra_left if extra_left > 0 else max(left + 1, left_block)
+    if right >= 0:
+        right_total = right + extra_right if extra_right > 0 else max(right + 1, m - left_block)
+
+    problem = solver.problem()
+    vector = problem.vector()
+    data_type = vector.data_type()
+    epsilon = float(numpy.finfo(data_type).eps)
+    single = data_type in (numpy.float32, numpy.complex64)
+    chol_eps = 1e-3 if single else 1e-8          # solver.py:1404-1407
+
+    hist = History(m, epsilon)
+    solver.cnv, solver.lmd, solver.res = hist.cnv, hist.lmd, hist.res
+    solver.err_lmd, solver.err_X = hist.err_lmd, hist.err_X
+    criteria = options.convergence_criteria
+    if criteria is None:
+        criteria = _default_criteria()
+
+    opA = problem.A()
+    opP = solver.preconditioner()
+    eng = engine
+    eng.begin(vector, m)
+    pool = _Pool(eng, 7)
+
+    # ---- initial block (solver.py:676-723) ---------------------------------------
+    X = pool.take(m)
+    X.fill_random()                      # host RNG stream: seeded runs start like the reference's
+    l = left_block
+    init_left = 0
+    if init[0] is not None:
+        init_left = min(l, init[0].nvec())
+        X.select(init_left)
+        init[0].select(init_left)
+        init[0].copy(X)
+    if init[1] is not None:
+        init_right = min(m - l, init[1].nvec())
+        X.select(init_right, init_left)
+        init[1].select(init_right)
+        init[1].copy(X)
+    X.select(m)
+    s = X.dots(X)
+    for i in numpy.nonzero(s == 0.0)[0]:
+        if verb > -1:
+            print('Zero initial guess, replacing with random')
+        X.select(1, int(i))
+        X.fill_random()
+    X.select(m)
+    eng.dots(X, X, eng.v_s2)
+    eng.scale_rsqrt(X, eng.v_s2)
+
+    # ---- constraints: eigenvectors already in the container (solver.py:743-775) ---
+    solver.eigenvectors = eigenvectors
+    Xc = eigenvectors
+    nc = Xc.nvec()
+    eng.reserve_constraints(nc + m)
+    if nc > 0:
+        eng.gram(Xc, Xc, eng.Gc.sub(0, 0, nc, nc))
+        _project_out(eng, X, Xc, nc, m)
+
+    # ---- drop linearly dependent initial vectors (solver.py:779-813) -------------
+    nx = m
+    eng.gram(X, X, eng.GB.sub(0, 0, m, m))
+    eng.piv_chol(eng.GB, m, 0, 1e-2)
+    dropped, ind = eng.fetch_chol(m)
+    if dropped > 0:
+        if verb > 0:
+            print('dropped %d initial vectors out of %d' % (dropped, nx))
+        nx -= dropped
+        T = pool.take(m)
+        if nx > 0:
+            T.select(nx)
+            eng.gather(X, ind[:nx], T)
+        T.select(dropped, nx)
+        T.fill_random()
+        if nc > 0:
+            _project_out(eng, T, Xc, nc, dropped)
+        T.select(m)
+        pool.give(X)
+        X = T
+        nx = m
+
+    # ---- Rayleigh-Ritz in the initial space (solver.py:815-830) ------------------
+    AX = pool.take(m)
+    opA.apply(X, AX)
+    eng.gram(X, X, eng.GB.sub(0, 0, m, m))
+    eng.gram(AX, X, eng.GA.sub(0, 0, m, m))
+    eng.ritz_initial(m)                   # generalised m x m problem -> coefficients CX, Ritz values lmdx
+    X, AX = _rotate(eng, pool, (X, AX), m, m)
+
+    # ---- main loop ------------------------------------------------------------------
+    max_iter = options.max_iter
+    min_iter = options.min_iter
+    if max_iter < 0:
+        max_iter = 100
+    solver.iteration = 0
+    Z = AZ = None
+    nz = 0
+    W = None
+
+    while True:
+        maxit = 0
+        if left != 0 and lay.left_block > 0:
+            maxit = numpy.amax(hist.iterations[:lay.left_block])
+        if right != 0 and lay.left_block < m:
+            maxit = max(maxit, numpy.amax(hist.iterations[lay.left_block:]))
+        if maxit >= max_iter:
+            if verb > -1:
+                print('iterations limit of %d exceeded, terminating' % max_iter)
+            break
+        if verb > 0:
+            print('------------- iteration %d' % solver.iteration)
+
+        nx, ix = lay.nx, lay.ix
+        X.select(nx)
+        AX.select(nx)
+
+        # Rayleigh quotients, orthonormality check, residuals (solver.py:854-974)
+        eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
+        eng.gram(X, X, eng.XBX.sub(0, 0, nx, nx))
+        eng.ritz_check(nx)                                   # -> v_lmd, rv_err, rv_no
+        W = pool.take(nx)
+        _residuals(eng, W, X, AX, Xc, nc, nx)
+        new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
+        if verb > 2:
+            print('Ritz values error: %.1e' % rv_err)
+            print('Ritz vectors non-orthonormality: %.1e' % rv_no)
+        if max(rv_err, rv_no) > math.sqrt(epsilon) or not numpy.all(numpy.isfinite(new_lmd)):
+            if verb > 0:
+                print('restarting...')
+            hist.rec = 0
+            nz = 0
+            X, AX = _restart(eng, pool, opA, X, AX, nx)
+            eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
+            eng.gram(X, X, eng.XBX.sub(0, 0, nx, nx))
+            eng.ritz_check(nx)
+            W.select(nx)
+            _residuals(eng, W, X, AX, Xc, nc, nx)
+            new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
+
+        hist.record_ritz_values(ix, new_lmd)
+        hist.res[ix:ix + nx] = numpy.sqrt(abs(res2))
+        hist.kinematic_estimates(ix, nx)
+        hist.residual_estimates(lay)
+        hist.update_floors_and_clusters(lay, solver.iteration)
+        if verb > 1:
+            _print_table(solver, hist, m)
+
+        lcon, rcon = hist.count_converged(
+            solver, lay, criteria,
+            (left, right, largest, sigma, min_iter, options.detect_stagnation, solver.iteration))
+
+        # lock converged pairs (solver.py:1197-1270)
+        if lcon > 0:
+            _record_converged(solver, hist, ix, ix + lcon)
+            nc = _lock(eng, X, Xc, nc, 0, lcon)
+        if rcon > 0:
+            _record_converged(solver, hist, ix + nx - rcon, ix + nx)
+            nc = _lock(eng, X, Xc, nc, nx - rcon, rcon)
+        solver.lcon += lcon
+        solver.rcon += rcon
+
+        # stopping tests (solver.py:1272-1298)
+        if options.stopping_criteria is not None and options.stopping_criteria.satisfied(solver):
+            return 0
+        if largest and right > 0 and solver.lcon + solver.rcon >= right:
+            return 0
+        left_done = left >= 0 and solver.lcon >= left
+        right_done = right >= 0 and solver.rcon >= right
+        if left_done and right_done:
+            return 0
+        if sigma is not None:
+            lmd, err_lmd = hist.lmd, hist.err_lmd
+            if right_done:
+                i = ix + lcon
+                if lmd[i] > 0 and err_lmd[0, i] != -1.0 and err_lmd[0, i] < lmd[i] / 4:
+                    return 4
+            if left_done:
+                i = ix + nx - rcon - 1
+                if lmd[i] < 0 and err_lmd[0, i] != -1.0 and err_lmd[0, i] < -lmd[i] / 4:
+                    return 5
+        if eigenvectors.nvec() > options.max_quota * eigenvectors.dimension():
+            return 1
+
+        # shrink the active window (solver.py:1300-1313)
+        iy, ny = ix, nx                      # the residual block still has one vector per OLD iterate
+        lay.leftX -= lcon
+        lay.rightX -= rcon
+        lay.ix += lcon
+        lay.nx -= lcon + rcon
+        ix, nx = lay.ix, lay.nx
+        x0 = lcon                            # first active vector inside the (compact) device blocks
+        X.select(nx, x0)
+        AX.select(nx, x0)
+
+        # search directions: preconditioned residuals (solver.py:1315-1319)
+        if opP is None:
+            Y = W
+        else:
+            Y = pool.take(ny)
+            W.select(ny)
+            opP.apply(W, Y)
+            pool.give(W)
+        W = None
+        Y.select(ny)
+
+        # conjugation to the previous directions (solver.py:1321-1351)
+        if nz > 0:
+            Z.select(nz)
+            AZ.select(nz)
+            eng.gram(Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
+            eng.gram(Y, Z, eng.ZBY.sub(0, 0, nz, ny))
+            eng.dots(Y, Y, eng.v_s2)
+            eng.dots(Z, Z, eng.v_t2)
+            eng.conjugation(nz, ny)               # uses the Ritz values of the OLD window, v_lmd[0:ny]
+            eng.update(Y, Z, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
+
+        # orthogonalise to X and to the locked vectors, normalise (solver.py:1360-1381)
+        if nx > 0:
+            eng.gram(Y, X, eng.T1.sub(0, 0, nx, ny))
+            eng.update(Y, X, eng.T1.sub(0, 0, nx, ny), -1.0, 1.0)
+        if nc > 0:
+            _project_out(eng, Y, Xc, nc, ny)
+        eng.dots(Y, Y, eng.v_s2)
+        eng.scale_rsqrt(Y, eng.v_s2)
+
+        # Gram matrix of (X, Y) and its pivoted Cholesky factor (solver.py:1375-1435)
+        nxy = nx + ny
+        if nx > 0:
+            eng.copy_small(eng.XBX.sub(x0, x0, nx, nx), eng.GB.sub(0, 0, nx, nx))
+            eng.gram(Y, X, eng.GB.sub(0, nx, nx, ny))
+        eng.gram(Y, Y, eng.GB.sub(nx, nx, ny, ny))
+        eng.mirror_upper(eng.GB, nx, ny)
+        eng.piv_chol(eng.GB, nxy, nx, chol_eps)
+        dropped, ind = eng.fetch_chol(nxy)
+        if dropped > 0 and verb > 0:
+            print('dropped %d search directions out of %d' % (dropped, ny))
+        ny -= dropped
+        if ny < 1:
+            if verb > -1:
+                print('no search directions left, terminating')
+            return 3
+        nxy = nx + ny
+        Yp = pool.take(ny)
+        eng.gather(Y, ind[nx:nxy] - nx, Yp)
+        pool.give(Y)
+        Y = Yp
+
+        # A-Gram matrix of (X, Y) (solver.py:1437-1454)
+        AY = pool.take(ny)
+        opA.apply(Y, AY)
+        if nx > 0:
+            eng.copy_small(eng.XAX.sub(x0, x0, nx, nx), eng.GA.sub(0, 0, nx, nx))
+            eng.gram(AY, X, eng.GA.sub(0, nx, nx, ny))
+        eng.gram(AY, Y, eng.GA.sub(nx, nx, ny, ny))
+        eng.mirror_upper(eng.GA, nx, ny)
+
+        # next block layout: integers only, known before the Ritz problem is solved
+        new, shift_left, shift_right, left_ratio = next_layout(
+            lay, ny, nxy, lcon, rcon, solver.lcon, solver.rcon, left, right, left_total, right_total,
+            left_ratio)
+        if verb > 2:
+            print('left X: was %d, now %d' % (lay.leftX, new.leftX))
+            print('right X: was %d, now %d' % (lay.rightX, new.rightX))
+            print('new ix %d, new nx %d, nxy %d' % (new.ix, new.nx, nxy))
+        nz_new = nxy - new.leftX - new.rightX
+
+        # Rayleigh-Ritz (solver.py:1456-1493, 1589-1607), all on the device
+        eng.rayleigh_ritz(nx, ny, lay.leftX, lay.rightX, new.leftX, new.rightX)
+        change, predicted = eng.fetch_estimates(nx)
+        hist.push_record(ix, nx, predicted, change)
+        hist.shift(lay.left_block, new.left_block, shift_left, shift_right)
+
+        # new X, Z and their images (solver.py:1609-1656); buffers rotate, nothing is copied back
+        nxn = new.nx
+        Xn = pool.take(nxn)
+        _combine(eng, Xn, X, Y, eng.CX, nx, ny, nxn)
+        if nz_new > 0:
+            if Z is None:
+                Z, AZ = pool.take(nz_new), pool.take(nz_new)
+            Z.select(nz_new)
+            AZ.select(nz_new)
+            _combine(eng, Z, X, Y, eng.CZ, nx, ny, nz_new)
+        pool.give(X, Y)
+        AXn = pool.take(nxn)
+        _combine(eng, AXn, AX, AY, eng.CX, nx, ny, nxn)
+        if nz_new > 0:
+            _combine(eng, AZ, AX, AY, eng.CZ, nx, ny, nz_new)
+        pool.give(AX, AY)
+        X, AX = Xn, AXn
+        nz = nz_new
+        lay = new
+        solver.iteration += 1
+
+    return 2
+
+
+# ---------------------------------------------------------------------------------------
+def _default_criteria():
+    class _Kinematic:
+        tolerance = 1e-3
+        error = 'kinematic eigenvector error'
+
+        def satisfied(self, solver, i):
+            err = solver.convergence_data(self.error, i)
+            return err >= 0 and err <= self.tolerance
+    return _Kinematic()
+
+
+def _project_out(eng, V, Xc, nc, nv):
+    """V <- V - Xc (2I - Gc) (Xc^T V)  (solver.py:774-775, 962-966, 1370-1371)."""
+    Xc.select(nc)
+    T = eng.TC.sub(0, 0, nc, nv)
+    Q = eng.QC.sub(0, 0, nc, nv)
+    eng.gram(V, Xc, T)
+    eng.constraint_coeffs(nc, nv)
+    eng.update(V, Xc, Q, -1.0, 1.0)
+
+
+def _residuals(eng, W, X, AX, Xc, nc, nx):
+    """W = AX - X diag(lmd), projected off the locked vectors; squared norms -> v_s2."""
+    eng.residual(W, AX, X, eng.v_lmd)
+    if nc > 0:
+        _project_out(eng, W, Xc, nc, nx)
+    eng.dots(W, W, eng.v_s2)
+
+
+def _rotate(eng, pool, blocks, k, mout):
+    """blocks <- blocks . CX[:k, :mout] through fresh buffers (no copy back)."""
+    out = []
+    for blk in blocks:
+        new = pool.take(mout)
+        blk.select(k)
+        eng.update(new, blk, eng.CX.sub(0, 0, k, mout), 1.0, 0.0)
+        pool.give(blk)
+        out.append(new)
+    return out
+
+
+def _combine(eng, out, X, Y, C, nx, ny, mout):
+    """out = X . C[:nx] + Y . C[nx:nx+ny]."""
+    out.select(mout)
+    if nx > 0:
+        eng.update(out, X, C.sub(0, 0, nx, mout), 1.0, 0.0)
+        eng.update(out, Y, C.sub(nx, 0, ny, mout), 1.0, 1.0)
+    else:
+        eng.update(out, Y, C.sub(0, 0, ny, mout), 1.0, 0.0)
+
+
+def _restart(eng, pool, opA, X, AX, nx):
+    """Loss of orthonormality among the iterates (solver.py:877-920): orthonormalise X
+    by its SVD, recompute AX and redo the Rayleigh-Ritz procedure in span(X)."""
+    X.select(nx)
+    X.svd()
+    AX.select(nx)
+    opA.apply(X, AX)
+    eng.gram(X, X, eng.GB.sub(0, 0, nx, nx))
+    eng.gram(AX, X, eng.GA.sub(0, 0, nx, nx))
+    eng.ritz_initial(nx)
+    return _rotate(eng, pool, (X, AX), nx, nx)
+
+
+def _record_converged(solver, hist, i0, i1):
+    solver.eigenvalues = numpy.concatenate((solver.eigenvalues, hist.lmd[i0:i1]))
+    solver.eigenvalue_errors.append(hist.err_lmd[:, i0:i1])
+    solver.eigenvector_errors.append(hist.err_X[:, i0:i1])
+    solver.residual_norms = numpy.concatenate((solver.residual_norms, hist.res[i0:i1]))
+    solver.convergence_status = numpy.concatenate((solver.convergence_status, hist.cnv[i0:i1]))
+
+
+def _lock(eng, X, Xc, nc, first, count):
+    """Append `count` iterates starting at `first` to the locked set and extend its Gram
+    matrix by the new row and column blocks (solver.py:1208-1230)."""
+    eng.reserve_constraints(nc + count)
+    X.select(count, first)
+    Xc.select(nc)
+    if nc > 0:
+        eng.gram(X, Xc, eng.Gc.sub(0, nc, nc, count))
+    Xc.append(X)
+    nc_new = nc + count
+    Xc.select(nc_new)
+    eng.gram(Xc, X, eng.Gc.sub(nc, 0, count, nc_new))
+    return nc_new
+
+
+def _print_table(solver, hist, m):
+    print('  eigenvalue   residual   estimated errors (kinematic/residual)      a.c.f.')
+    print('                             eigenvalue            eigenvector ')
+    for i in range(m):
+        print('%14e %8.1e  %8.1e / %8.1e    %.1e / %.1e  %.3e  %d' %
+              (hist.lmd[i], hist.res[i], hist.err_lmd[0, i], hist.err_lmd[1, i],
+               abs(hist.err_X[0, i]), abs(hist.err_X[1, i]), hist.acf[0, i], hist.cnv[i]))

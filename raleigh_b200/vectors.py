@@ -36,6 +36,7 @@ def _np_type(t):
 class Vectors:
     """Block of vectors resident in HBM.  dense_cublas.py:17-632."""
 
+    _rl_device_block = True           # marks blocks the device-resident solver driver (jcg.py) can run on
     HOST_RNG_MAX_ELEMENTS = 1 << 24   # above this fill_random() switches to the device RNG
     MIN_INC = 16      # capacity growth policy of the reference (dense_cublas.py:424-425)
     MAX_INC = 1024

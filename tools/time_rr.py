@@ -1,0 +1,101 @@
+"""Device time of the small-matrix kernels of the Rayleigh-Ritz step (CUDA events, warm cache):
+pivoted Cholesky, cluster Jacobi, the whole rl_rr_solve, at the block sizes of the BASELINE configs.
+
+    python tools/time_rr.py [--out gpurun_out/time_rr.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import raleigh_b200  # noqa: E402,F401
+from raleigh_b200._lib import lib, check  # noqa: E402
+from raleigh_b200 import device as dev  # noqa: E402
+
+
+def timeit(fn, reps=20):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def up(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=None)
+    args = ap.parse_args()
+    out = open(args.out, 'w') if args.out else None
+
+    def emit(**rec):
+        line = json.dumps(rec)
+        print(line, flush=True)
+        if out:
+            out.write(line + '\n')
+
+    st = dev.stream
+    for m in (16, 32, 64, 120, 128, 160):
+        n = 2 * m
+        rng = np.random.RandomState(m)
+        N = 6 * n
+        V = rng.randn(N, n)
+        V[:, :m], _ = np.linalg.qr(V[:, :m])
+        V[:, m:] -= V[:, :m] @ (V[:, :m].T @ V[:, m:])
+        V[:, m:] /= np.linalg.norm(V[:, m:], axis=0)
+        A = np.diag(np.linspace(1.0, 1000.0, N))
+        GB, GA = V.T @ V, V.T @ A @ V
+        dGB0, dGA = up(GB), up(GA)
+        dGB, dA0 = torch.zeros_like(dGB0), torch.zeros_like(dGB0)
+        ind = torch.zeros(n, dtype=torch.int32, device='cuda')
+        info = torch.zeros(8, dtype=torch.int32, device='cuda')
+
+        def chol():
+            dGB.copy_(dGB0)
+            check(lib.rl_rr_piv_chol(dGB.data_ptr(), dA0.data_ptr(), n, n, m, 1e-8, ind.data_ptr(), info.data_ptr(), st()))
+        t_chol = timeit(chol)
+        assert int(info[0]) == 0
+        wsb = lib.rl_rr_solve_ws_bytes(n)
+        ws = torch.zeros(wsb // 8 + 8, dtype=torch.float64, device='cuda')
+        cx, cz = torch.zeros(n, n, dtype=torch.float64, device='cuda'), torch.zeros(n, n, dtype=torch.float64, device='cuda')
+        lx, lz, est = (torch.zeros(2 * n, dtype=torch.float64, device='cuda') for _ in range(3))
+
+        def rr():
+            check(lib.rl_rr_solve(dGA.data_ptr(), dGB.data_ptr(), n, m, m, m, 0, m, 0, cx.data_ptr(), n, cz.data_ptr(), n,
+                                  lx.data_ptr(), lz.data_ptr(), est.data_ptr(), n, ws.data_ptr(), wsb, info.data_ptr(), st()))
+        t_rr = timeit(rr)
+        sweeps_rr = int(info[0])
+        w, Q = torch.zeros(n, dtype=torch.float64, device='cuda'), torch.zeros(n, n, dtype=torch.float64, device='cuda')
+        ewsb = lib.rl_small_eigh_ws_bytes(n)
+        ews = torch.zeros(ewsb // 8 + 8, dtype=torch.float64, device='cuda')
+        G = rng.randn(n, n)
+        G = up(G + G.T)
+        res = {}
+        for p in (m, n):
+            def eig():
+                check(lib.rl_small_eigh(G.data_ptr(), n, p, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+            res['eigh_%d_ms' % p] = round(timeit(eig, 10), 4)
+            res['eigh_%d_sweeps' % p] = int(info[0])
+        B = up(rng.randn(n, n))
+
+        def trsm():
+            check(lib.rl_small_trsm(0, dGB.data_ptr(), n, n, B.data_ptr(), n, n, st()))
+        t_trsm = timeit(trsm)
+        emit(block=m, nxy=n, piv_chol_ms=round(t_chol, 4), rr_solve_ms=round(t_rr, 4), rr_final_eigh_sweeps=sweeps_rr,
+             trsm_ms=round(t_trsm, 4), **res)
+
+
+if __name__ == '__main__':
+    main()
