@@ -178,9 +178,11 @@ int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N,
 
 /* Tensor-core path of the same product for fp32 (tcgen05.mma kind::tf32, TMEM
  * accumulators, TMA-fed), fp32-accurate through the 3xTF32 split
- * X.A ~= Xhi.Ahi + Xhi.Alo + Xlo.Ahi.  `a_lo` is the low part of the data
- * matrix, produced once per matrix version by rl_split_tf32 (same shape and
- * lda as `a`); the block's low part is built per call inside `ws`.
+ * X.A ~= Xhi.Ahi + Xhi.Alo + Xlo.Ahi.  a_lo == NULL (default): the low parts of
+ * both operands are computed in shared memory by four extra warps, HBM traffic
+ * is the data matrix once.  a_lo != NULL: materialised low part of the data
+ * matrix from rl_split_tf32 (same shape and lda as `a`; A/B variant, streams the
+ * matrix twice); the block's low part is then built per call inside `ws`.
  * Requirements: 16-byte aligned bases, lda and ldx multiples of 4
  * (rl_dense_apply_tc_supported); any M, N, k. */
 int rl_dense_apply_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx);
@@ -319,19 +321,58 @@ int rl_rr_select(const double* q, int64_t ldq, const double* w, int64_t nxy, int
  * (csrc/jacobi.cu); larger: the cooperative-grid kernel behind rl_syevj.  w ascending,
  * q[i*ldq + j] = component i of eigenvector j; g is read only (both triangles, averaged). */
 int rl_syevj_cluster_max_n(void);
+/* orders up to rl_syevj_grid_max_n() run the same method on the whole GPU (cooperative launch,
+ * columns in L2, one warp per pair); factor_mode != 0: g is the upper Cholesky factor U of the
+ * matrix to decompose and the rotations act on its rows (no shift, relative accuracy);
+ * tol: pairs rotate while |<p, q>| > tol |p| |q| (<= 0: sqrt(n) eps) */
+int rl_syevj_grid_max_n(void);
 size_t rl_syevj_cluster_ws_bytes(int64_t n);
-int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq,
-                     void* ws, size_t ws_bytes, int* info_d, void* stream);
+int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, int factor_mode, double tol, double* w,
+                     double* q, int64_t ldq, void* ws, size_t ws_bytes, int* info_d, void* stream);
 size_t rl_small_eigh_ws_bytes(int64_t n);
 int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq,
                   void* ws, size_t ws_bytes, int* info_d, void* stream);
+int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double* w, double* q, int64_t ldq,
+                         void* ws, size_t ws_bytes, int* info_d, void* stream);
+/* unpivoted Cholesky factorisation G = U^T U of an n x n fp64 matrix in place (upper factor, zeros
+ * below; numpy.linalg.cholesky at partial_svd.py:192), blocked: diagonal blocks in shared memory,
+ * panels by rl_small_trsm, trailing update by rl_small_gemm.  info_d[0] = 0 or 1 + index of the
+ * first non-positive pivot. */
+int rl_small_potrf(double* a, int64_t ld, int64_t n, int* info_d, void* stream);
 /* the whole Rayleigh-Ritz step (solver.py:1456-1493, 1589-1607): transform, pre-rotation, eigh,
- * estimates, back-transformation, coefficient blocks.  est: dX at est[0..nx), dlmd at est[nmax..) */
+ * estimates, back-transformation, coefficient blocks.  est: dX at est[0..nx), dlmd at est[nmax..);
+ * eig_tol: stopping tolerance of the eigensolver (<= 0: working precision) */
 size_t rl_rr_solve_ws_bytes(int64_t nmax);
 int rl_rr_solve(const double* ga, const double* u, int64_t ld, int64_t nx, int64_t ny,
                 int64_t leftX, int64_t rightX, int64_t leftXn, int64_t rightXn, double* cx,
                 int64_t ldcx, double* cz, int64_t ldcz, double* lmdx, double* lmdz, double* est,
-                int64_t nmax, void* ws, size_t ws_bytes, int* info_d, void* stream);
+                int64_t nmax, double eig_tol, void* ws, size_t ws_bytes, int* info_d, void* stream);
+
+
+/* ---- device-resident post-processing of the partial SVD ---------
+ * PartialSVD._finalize_svd (interfaces/partial_svd.py:163-235) factorises nsv x nsv matrices
+ * with scipy.linalg eigh / cholesky / svd / inv on the host.  Here: Gram matrix on the device,
+ * a Gershgorin certificate (or the eigenvalues) of its diagonally scaled form for the
+ * conditioning test (:171-182), ONE symmetric eigen-decomposition on the device for
+ * U = chol(G), svd(U), inv(U) (:190-197: A v = (Av q Sigma^-1) Sigma q^T), coefficient blocks. */
+/* fp64 small matrix -> typed block (optionally transposed), and back */
+int rl_small_to_block(int dtype, const double* src, int64_t lds, int64_t rows, int64_t cols,
+                      int trans, void* dst, int64_t ldd, void* stream);
+int rl_block_to_small(int dtype, const void* src, int64_t lds, int64_t rows, int64_t cols,
+                      double* dst, int64_t ldd, void* stream);
+/* out3 = { max_i sum_{j != i} |S_ij|, min_i G_ii, max_i G_ii },  S = D^-1/2 G D^-1/2 */
+int rl_psvd_gershgorin(const double* g, int64_t ld, int64_t n, double* out3, void* stream);
+int rl_psvd_scale(const double* g, int64_t ld, int64_t n, double* s, int64_t lds, void* stream);
+/* (w ascending, Q) -> sigma descending, q = Q reordered, cs = q diag(1 / sigma) */
+int rl_psvd_coeffs(const double* qin, int64_t ldq, const double* w, int64_t n, double* q,
+                   double* cs, int64_t ldo, double* sigma, void* stream);
+
+/* pieces of the conditioning test of _finalize_svd (partial_svd.py:171-182) without eigenvalues:
+ * with G = U^T U and S = D^-1/2 G D^-1/2,  lambda_min(S) >= 1 / sum_ij d_i (U^-1)_ij^2.
+ * rl_small_set_identity: a = I;  rl_psvd_invbound: out[0] = sum_ij g_ii uinv_ij^2 */
+int rl_small_set_identity(double* a, int64_t ld, int64_t n, void* stream);
+int rl_psvd_invbound(const double* uinv, int64_t ldu, const double* g, int64_t ldg, int64_t n,
+                     double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,11 +112,42 @@ def _cond_inverse(U, A0, ind, p):
     return rq / lmax
 
 
-def jacobi_eigh(G, max_sweeps=40):
+def jacobi_layout(n):
+    """(cluster size C, columns per block W) chosen by rl_syevj_cluster for order n."""
+    npairs = (n + 1) // 2
+    length = (n + 63) // 64 * 64
+    c = 1
+    while True:
+        w = (npairs + c - 1) // c
+        if (w <= 16 or (c == 8 and w <= 32)) and 4 * w * length * 8 <= 200 * 1024:
+            return c, max(w, 1)
+        if c == 8:
+            raise ValueError('order %d too large for the cluster kernel' % n)
+        c *= 2
+
+
+def _rotate(B, p, q, tol2):
+    bp, bq = B[:, p].copy(), B[:, q].copy()
+    alpha, beta, gamma = bp @ bp, bq @ bq, bp @ bq
+    if not gamma * gamma > tol2 * alpha * beta:
+        return False
+    delta = beta - alpha
+    h = delta * delta + 4.0 * gamma * gamma
+    t = (2.0 if delta >= 0 else -2.0) * gamma / (abs(delta) + np.sqrt(h))
+    c = 1.0 / np.sqrt(1.0 + t * t)
+    s = c * t
+    B[:, p], B[:, q] = c * bp - s * bq, s * bp + c * bq
+    return True
+
+
+def jacobi_eigh(G, max_sweeps=48):
     """Symmetric eigen-decomposition by ONE-SIDED Jacobi on the shifted matrix
     B = G + sigma I (sigma from Gershgorin discs, so that B is positive definite):
     column rotations orthogonalise B V; then B V = Q diag(lambda + sigma).  Same
-    algorithm as csrc/jacobi.cu.  Returns (w ascending, Q columns, sweeps)."""
+    algorithm and the same two-level rotation order as csrc/jacobi.cu (blocks of W
+    columns, two per CTA of a cluster of C): per sweep first the pairs inside every
+    block, then 2C-1 outer rounds of block-against-block pairs with the blocks moving
+    round-robin between the CTAs.  Returns (w ascending, Q columns, sweeps)."""
     n = G.shape[0]
     if n == 0:
         return np.zeros(0), np.zeros((0, 0)), 0
@@ -128,40 +159,60 @@ def jacobi_eigh(G, max_sweeps=40):
     sigma = 0.0
     if low <= 1e-3 * norm:
         sigma = -low + 1e-2 * norm
-    if norm == 0.0:
-        return np.zeros(n), np.eye(n), 0
-    B = G + sigma * np.eye(n)
+    if not norm > 0.0:
+        sigma = 1.0
+    C, W = jacobi_layout(n)
+    ncols = 2 * C * W
+    B = np.zeros((n, ncols))
+    B[:, :n] = G + sigma * np.eye(n)
     tol = np.sqrt(n) * np.finfo(np.float64).eps
-    P = n + (n & 1)
+    tol2 = tol * tol
+    # block b of CTA c: slot (c, side); blocks[c][side] = list of column ids
+    blocks = [[list(range((2 * c + s) * W, (2 * c + s + 1) * W)) for s in range(2)] for c in range(C)]
+    P = (W + 1) & ~1
     sweeps = 0
     for sweep in range(max_sweeps):
         rotated = False
         for t in range(P - 1):
-            for i in range(P // 2):
-                if i == 0:
-                    p, q = P - 1, t
-                else:
-                    p, q = (t + i) % (P - 1), (t - i + P - 1) % (P - 1)
-                if p > q:
-                    p, q = q, p
-                if q >= n:
-                    continue
-                bp, bq = B[:, p], B[:, q]
-                alpha, beta, gamma = bp @ bp, bq @ bq, bp @ bq
-                if abs(gamma) <= tol * np.sqrt(alpha * beta) or gamma == 0.0:
-                    continue
-                rotated = True
-                zeta = (beta - alpha) / (2.0 * gamma)
-                tt = np.sign(zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta)) if zeta != 0 else 1.0
-                c = 1.0 / np.sqrt(1.0 + tt * tt)
-                s = c * tt
-                B[:, p], B[:, q] = c * bp - s * bq, s * bp + c * bq
+            for c in range(C):
+                for side in range(2):
+                    cols = blocks[c][side]
+                    for i in range(P // 2):
+                        if i == 0:
+                            a, b = P - 1, t
+                        else:
+                            a, b = (t + i) % (P - 1), (t - i + P - 1) % (P - 1)
+                        if a > b:
+                            a, b = b, a
+                        if b >= W:
+                            continue
+                        rotated |= _rotate(B, cols[a], cols[b], tol2)
+        for o in range(2 * C - 1 if C > 1 else 1):
+            for r in range(W):
+                for c in range(C):
+                    A_, B_ = blocks[c]
+                    for w in range(W):
+                        rotated |= _rotate(B, A_[w], B_[(w + r) % W], tol2)
+            if C > 1:
+                new = [[None, None] for _ in range(C)]
+                for c in range(C):
+                    if c == 0:
+                        new[0][0] = blocks[0][0]
+                        new[1][0] = blocks[0][1]
+                    else:
+                        if c == C - 1:
+                            new[c][1] = blocks[c][0]
+                        else:
+                            new[c + 1][0] = blocks[c][0]
+                        new[c - 1][1] = blocks[c][1]
+                blocks = new
         sweeps = sweep + 1
         if not rotated:
             break
     norms = np.sqrt(np.sum(B * B, axis=0))
-    w = norms - sigma
-    Q = B / np.where(norms > 0, norms, 1.0)[None, :]
+    real = norms > 0
+    w = norms[real] - sigma
+    Q = B[:, real] / norms[real][None, :]
     order = np.argsort(w, kind='stable')
     return w[order], Q[:, order], sweeps
 

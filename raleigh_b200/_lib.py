@@ -107,12 +107,22 @@ PROTOTYPES = {
     'rl_rr_select': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     'rl_syevj_cluster_max_n': (c_int, []),
     'rl_syevj_cluster_ws_bytes': (c_sz, [c_i64]),
-    'rl_syevj_cluster': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    'rl_syevj_grid_max_n': (c_int, []),
+    'rl_syevj_cluster': (c_int, [c_vp, c_i64, c_i64, c_int, c_dbl, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    'rl_small_set_identity': (c_int, [c_vp, c_i64, c_i64, c_vp]),
+    'rl_psvd_invbound': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'rl_small_eigh_factor': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    'rl_small_potrf': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     'rl_small_eigh_ws_bytes': (c_sz, [c_i64]),
     'rl_small_eigh': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
     'rl_rr_solve_ws_bytes': (c_sz, [c_i64]),
     'rl_rr_solve': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
-                            c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
+                            c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_sz, c_vp, c_vp]),
+    'rl_small_to_block': (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_vp]),
+    'rl_block_to_small': (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    'rl_psvd_gershgorin': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'rl_psvd_scale': (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    'rl_psvd_coeffs': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'rl_syevj_ws_bytes': (c_sz, [c_i64]),
     'rl_syevj': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, ctypes.POINTER(c_int), c_vp]),
 }

@@ -276,6 +276,27 @@ def hook_device_solver():
     rsolver.Solver._solve = _solve
 
 
+def hook_device_finalize_svd():
+    """PartialSVD._finalize_svd (partial_svd.py:163-235) -> psvd.finalize_svd whenever the vectors are
+    raleigh_b200 blocks and the device solver is on; the reference's host LAPACK version otherwise."""
+    try:
+        import raleigh.interfaces.partial_svd as rpsvd
+    except ImportError:
+        return
+    cls = rpsvd.PartialSVD
+    if getattr(cls, '_reference_finalize_svd', None) is not None:
+        return
+    cls._reference_finalize_svd = staticmethod(cls._finalize_svd)
+
+    def _finalize(v, Av, eps):
+        if DEVICE_SOLVER and hasattr(v, '_rl_device_block'):
+            from . import psvd
+            return psvd.finalize_svd(v, Av, eps)
+        return cls._reference_finalize_svd(v, Av, eps)
+
+    cls._finalize_svd = staticmethod(_finalize)
+
+
 def install(reference_path=None, sparse=True, dense=True):
     """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.
     Raises ImportError if the reference package cannot be found."""
@@ -304,4 +325,5 @@ def install(reference_path=None, sparse=True, dense=True):
     shim_scipy()
     shim_host_hotspots()
     hook_device_solver()
+    hook_device_finalize_svd()
     return raleigh

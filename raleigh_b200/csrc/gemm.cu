@@ -53,8 +53,8 @@ int rl_dense_apply_tc(const void* a, const void* a_lo, int64_t lda, int64_t M, i
     if (k == 0 || (transp ? N : M) == 0) return 0;
     if (!gemm_tc_supported(a, lda, x, ldx) || !host_aligned16(a_lo)) return RL_E_ARG;
     cudaStream_t st = as_stream(stream);
-    // algorithmic traffic: the hi and lo copies of the data matrix are both streamed
-    Span span(PK_DENSE_APPLY_TC, st, (2.0 * M * N + 1.0 * k * (M + N)) * 4.0, 2.0 * M * N * k);
+    // algorithmic traffic: the data matrix once, the blocks in and out
+    Span span(PK_DENSE_APPLY_TC, st, (1.0 * M * N + 1.0 * k * (M + N)) * 4.0, 2.0 * M * N * k);
     return gemm_tc((const float*)a, (const float*)a_lo, lda, M, N, (const float*)x, ldx, (float*)y, ldy, k, transp,
                    alpha, beta, ws, ws_bytes, st);
 }

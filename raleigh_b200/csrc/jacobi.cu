@@ -58,72 +58,115 @@ jacobi_shift_kernel(const double* __restrict__ G, int64_t ld, int n, double* __r
     }
 }
 
+// Rotation of a column pair from its three dot products.  One rsqrt for sqrt(delta^2 + 4 gamma^2), one
+// division and one rsqrt for the cosine: the dependent chain of double-precision special functions is
+// what a round costs, so the textbook form (two divisions, two square roots, one reciprocal) is avoided.
+__device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol2, double& c,
+                                                double& s) {
+    c = 1.0; s = 0.0;
+    if (!(gamma * gamma > tol2 * alpha * beta)) return false;      // also false for zero (padding) columns
+    const double delta = beta - alpha;
+    const double h = fma(delta, delta, 4.0 * gamma * gamma);
+    const double den = fabs(delta) + h * rsqrt(h);
+    const double t = (delta >= 0.0 ? 2.0 : -2.0) * gamma / den;
+    c = rsqrt(fma(t, t, 1.0));
+    s = c * t;
+    return true;
+}
+
 // NJ = (padded column length) / 64: a lane holds NJ 16-byte chunks (2 doubles) of each column,
 // chunk index = lane + 32 * j -- consecutive lanes read consecutive 16-byte words (no bank conflicts).
+//
+// Two-level tournament.  Every CTA of the cluster holds two BLOCKS of W columns (A and B).  A sweep is
+//   (1) W-1 rounds among the columns of each block (circle method on indices, in place),
+//   (2) 2C-1 outer rounds; in each, W rounds pair A_w with B_(w+r) -- A_w stays in the registers of
+//       warp w, only B columns go through shared memory -- and then the blocks move to the
+//       neighbouring CTAs (circle method on blocks) through distributed shared memory, double buffered.
+// All (W-1) + (2C-1) W = n-1 rounds of a sweep cost one __syncthreads each; the cluster barrier
+// (~400 cycles + DSMEM traffic) is paid 2C-1 times per sweep instead of n-1 times.
 // (at most 16 warps per CTA up to n = 256, 20 at n = 320: see rl_syevj_cluster)
 template <int NJ>
 __global__ void __launch_bounds__(NJ == 5 ? 640 : 512)
-jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int npairs, int W,
+jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, int factor_mode, double tol,
                       const double* __restrict__ par, double* __restrict__ wtmp, double* __restrict__ qtmp,
                       int* __restrict__ info) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char jc_smem[];
     constexpr int LEN = 64 * NJ;                                 // padded column length (doubles)
-    double* buf = reinterpret_cast<double*>(jc_smem);            // [2][2W][LEN]
+    double* buf = reinterpret_cast<double*>(jc_smem);            // [2][2W][LEN]: A block = columns 0..W-1, B block = W..2W-1
     __shared__ int s_rot[32];
     __shared__ int s_flag[JC_MAX_SWEEPS][JC_MAX_CLUSTER];        // meaningful in CTA 0 only
+    __shared__ int s_any;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int rank = (int)cluster.block_rank();
-    const int csize = (int)cluster.num_blocks();
-    const int k = rank * W + w;                                  // global pair index
-    const bool active = w < W && k < npairs;
-    const double sigma = par[0];
+    const int C = (int)cluster.num_blocks();
+    const double sigma = factor_mode ? 0.0 : par[0];
     const size_t bufstride = (size_t)2 * W * LEN;
 
     for (int i = threadIdx.x; i < JC_MAX_SWEEPS * JC_MAX_CLUSTER; i += blockDim.x) (&s_flag[0][0])[i] = 0;
-    // initial columns: pair k holds columns 2k (top) and 2k+1 (bottom) of B = sym(G) + sigma I
-    if (w < W) {
-        for (int side = 0; side < 2; ++side) {
-            const int c = 2 * k + side;
-            double2* col = reinterpret_cast<double2*>(buf + ((size_t)(2 * w + side)) * LEN);
+    // initial columns of B = sym(G) + sigma I: CTA `rank` holds global columns [rank 2W, (rank+1) 2W)
+    for (int side = 0; side < 2; ++side) {
+        const int c = rank * 2 * W + side * W + w;
+        double2* col = reinterpret_cast<double2*>(buf + (size_t)(side * W + w) * LEN);
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int r0 = 2 * (lane + 32 * j);
-                double2 v = make_double2(0.0, 0.0);
-                if (k < npairs && c < n) {
-                    if (r0 < n) v.x = 0.5 * (G[(int64_t)r0 * ldg + c] + G[(int64_t)c * ldg + r0]) + (r0 == c ? sigma : 0.0);
-                    if (r0 + 1 < n) v.y = 0.5 * (G[(int64_t)(r0 + 1) * ldg + c] + G[(int64_t)c * ldg + r0 + 1]) + (r0 + 1 == c ? sigma : 0.0);
-                }
-                col[lane + 32 * j] = v;
+        for (int j = 0; j < NJ; ++j) {
+            const int r0 = 2 * (lane + 32 * j);
+            double2 v = make_double2(0.0, 0.0);
+            if (c < n && factor_mode) {             // column c of L = row c of the upper factor U
+                if (r0 < n) v.x = G[(int64_t)c * ldg + r0];
+                if (r0 + 1 < n) v.y = G[(int64_t)c * ldg + r0 + 1];
+            } else if (c < n) {
+                if (r0 < n) v.x = 0.5 * (G[(int64_t)r0 * ldg + c] + G[(int64_t)c * ldg + r0]) + (r0 == c ? sigma : 0.0);
+                if (r0 + 1 < n) v.y = 0.5 * (G[(int64_t)(r0 + 1) * ldg + c] + G[(int64_t)c * ldg + r0 + 1]) + (r0 + 1 == c ? sigma : 0.0);
             }
+            col[lane + 32 * j] = v;
         }
     }
     cluster.sync();
 
-    const double tol = sqrt((double)n) * 2.220446049250313e-16;
-    // destination slots of the rotated columns (the same permutation every round)
-    int dtk = 0, dts = 0, dbk = 0, dbs = 0;
-    if (npairs > 1) {
-        if (k == 0) { dtk = 0; dts = 0; dbk = 1; dbs = 0; }
+    const double tol2 = tol * tol;
+    // block movement of the outer circle tournament (the same every round):
+    // A: CTA 0 keeps it; CTA c sends it to the A slot of c+1; the last CTA moves it to its own B slot.
+    // B: CTA c sends it to the B slot of c-1; CTA 0 sends it to the A slot of CTA 1.
+    int a_rank = rank, a_side = 0, b_rank = rank, b_side = 1;
+    if (C > 1) {
+        if (rank == 0) { a_rank = 0; a_side = 0; b_rank = 1; b_side = 0; }
         else {
-            if (k == npairs - 1) { dtk = npairs - 1; dts = 1; } else { dtk = k + 1; dts = 0; }
-            dbk = k - 1; dbs = 1;
+            if (rank == C - 1) { a_rank = rank; a_side = 1; } else { a_rank = rank + 1; a_side = 0; }
+            b_rank = rank - 1; b_side = 1;
         }
-    } else { dtk = 0; dts = 0; dbk = 0; dbs = 1; }
+    }
+    // destination columns in both buffers (resolved once: mapa + address arithmetic stay out of the loop)
+    double2* dstA[2];
+    double2* dstB[2];
+    for (int b = 0; b < 2; ++b) {
+        double* la = buf + b * bufstride + (size_t)(a_side * W + w) * LEN;
+        double* lb = buf + b * bufstride + (size_t)(b_side * W + w) * LEN;
+        dstA[b] = reinterpret_cast<double2*>(C > 1 && a_rank != rank ? cluster.map_shared_rank(la, a_rank) : la);
+        dstB[b] = reinterpret_cast<double2*>(C > 1 && b_rank != rank ? cluster.map_shared_rank(lb, b_rank) : lb);
+    }
+    const int P = (W + 1) & ~1;                       // players of the intra-block tournament (one dummy if W is odd)
+    const int nouter = C > 1 ? 2 * C - 1 : 1;
     int cur = 0, sweep = 0, converged = 0;
-    const int rounds = npairs > 1 ? 2 * npairs - 1 : 1;
     for (; sweep < JC_MAX_SWEEPS; ++sweep) {
         int rot = 0;
-        for (int t = 0; t < rounds; ++t) {
-            if (active) {
-                const double2* ct = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(2 * w) * LEN);
-                const double2* cb = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(2 * w + 1) * LEN);
+        // (1) pairs inside each block
+        for (int t = 0; t < P - 1; ++t) {
+            for (int task = w; task < P; task += W) {
+                const int blk = task >= P / 2 ? 1 : 0;
+                const int i = task - blk * (P / 2);
+                int a, b;
+                if (i == 0) { a = P - 1; b = t; } else { a = (t + i) % (P - 1); b = (t - i + P - 1) % (P - 1); }
+                if (a > b) { const int x = a; a = b; b = x; }
+                if (b >= W) continue;                                   // dummy player
+                double2* cp = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)(blk * W + a) * LEN);
+                double2* cq = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)(blk * W + b) * LEN);
                 double2 p[NJ], q[NJ];
                 double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    p[j] = ct[lane + 32 * j];
-                    q[j] = cb[lane + 32 * j];
+                    p[j] = cp[lane + 32 * j];
+                    q[j] = cq[lane + 32 * j];
                     alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
                     beta = fma(q[j].x, q[j].x, beta); beta = fma(q[j].y, q[j].y, beta);
                     gamma = fma(p[j].x, q[j].x, gamma); gamma = fma(p[j].y, q[j].y, gamma);
@@ -134,78 +177,139 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int npai
                     beta += __shfl_xor_sync(0xffffffffu, beta, o);
                     gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
                 }
-                double c = 1.0, s = 0.0;
-                if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
+                double c, s;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
                     rot = 1;
-                    const double zeta = (beta - alpha) / (2.0 * gamma);
-                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    c = 1.0 / sqrt(1.0 + tt * tt);
-                    s = c * tt;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        double2 x, y;
+                        x.x = c * p[j].x - s * q[j].x; x.y = c * p[j].y - s * q[j].y;
+                        y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
+                        cp[lane + 32 * j] = x;
+                        cq[lane + 32 * j] = y;
+                    }
                 }
-                double* dt = buf + (cur ^ 1) * bufstride + (size_t)(2 * (dtk % W) + dts) * LEN;
-                double* db = buf + (cur ^ 1) * bufstride + (size_t)(2 * (dbk % W) + dbs) * LEN;
-                const int rt = dtk / W, rb = dbk / W;
-                double2* pt = reinterpret_cast<double2*>(rt == rank ? dt : cluster.map_shared_rank(dt, rt));
-                double2* pb = reinterpret_cast<double2*>(rb == rank ? db : cluster.map_shared_rank(db, rb));
+            }
+            __syncthreads();
+        }
+        // (2) pairs across blocks: W local rounds per outer round, then the blocks move on
+        for (int o = 0; o < nouter; ++o) {
+            double2* ca = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)w * LEN);
+            double2 p[NJ];
+            double alpha = 0.0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                p[j] = ca[lane + 32 * j];
+                alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) alpha += __shfl_xor_sync(0xffffffffu, alpha, o2);
+            for (int r = 0; r < W; ++r) {
+                int jb = w + r; if (jb >= W) jb -= W;
+                double2* cb = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)(W + jb) * LEN);
+                double2 q[NJ];
+                double beta = 0.0, gamma = 0.0;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    double2 a, b;
-                    a.x = c * p[j].x - s * q[j].x; a.y = c * p[j].y - s * q[j].y;
-                    b.x = s * p[j].x + c * q[j].x; b.y = s * p[j].y + c * q[j].y;
-                    pt[lane + 32 * j] = a;
-                    pb[lane + 32 * j] = b;
+                    q[j] = cb[lane + 32 * j];
+                    beta = fma(q[j].x, q[j].x, beta); beta = fma(q[j].y, q[j].y, beta);
+                    gamma = fma(p[j].x, q[j].x, gamma); gamma = fma(p[j].y, q[j].y, gamma);
                 }
-            }
-            if (t == rounds - 1) {
-                // sweep ends: did anybody rotate?  CTA-level OR, then one plain store per CTA into CTA 0
-                if (lane == 0) s_rot[w] = rot;
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                    beta += __shfl_xor_sync(0xffffffffu, beta, o2);
+                    gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
+                }
+                double c, s;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
+                    rot = 1;
+                    double na = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        double2 x, y;
+                        x.x = c * p[j].x - s * q[j].x; x.y = c * p[j].y - s * q[j].y;
+                        y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
+                        p[j] = x;
+                        cb[lane + 32 * j] = y;
+                        na = fma(x.x, x.x, na); na = fma(x.y, x.y, na);
+                    }
+                    // the norm of the register-resident column is recomputed, not updated: no drift
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o2);
+                    alpha = na;
+                }
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    int any = 0;
-                    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) any |= s_rot[i];
-                    int* f = cluster.map_shared_rank(&s_flag[sweep][rank], 0);
-                    *f = any;
+            }
+            if (C > 1) {
+                // A_w (registers) and B_w (shared memory) go to their next CTA, other buffer
+                const double2* cbw = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(W + w) * LEN);
+                double2* da = dstA[cur ^ 1];
+                double2* db = dstB[cur ^ 1];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    da[lane + 32 * j] = p[j];
+                    db[lane + 32 * j] = cbw[lane + 32 * j];
                 }
+                cluster.sync();
+                cur ^= 1;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) ca[lane + 32 * j] = p[j];
+                __syncthreads();
+            }
+        }
+        // did anybody rotate in this sweep?
+        if (lane == 0) s_rot[w] = rot;
+        __syncthreads();
+        int any = 0;
+        if (C > 1) {
+            if (threadIdx.x == 0) {
+                int a = 0;
+                for (int i = 0; i < W; ++i) a |= s_rot[i];
+                *cluster.map_shared_rank(&s_flag[sweep][rank], 0) = a;
             }
             cluster.sync();
-            cur ^= 1;
-        }
-        int any = 0;
-        {
             const int* f = cluster.map_shared_rank(&s_flag[sweep][0], 0);
-            for (int r = 0; r < csize; ++r) any |= f[r];
+            for (int r = 0; r < C; ++r) any |= f[r];
+        } else {
+            if (threadIdx.x == 0) {
+                int a = 0;
+                for (int i = 0; i < W; ++i) a |= s_rot[i];
+                s_any = a;
+            }
+            __syncthreads();
+            any = s_any;
+            __syncthreads();
         }
         if (!any) { converged = 1; ++sweep; break; }
     }
     // nobody may leave (and release its shared memory) while others still read the flags of CTA 0
     cluster.sync();
     // eigenvalue = column norm - sigma, eigenvector = column / norm; slots in arbitrary order, sorted later
-    if (w < W) {
-        for (int side = 0; side < 2; ++side) {
-            const int slot = 2 * (rank * W + w) + side;
-            const double2* col = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(2 * w + side) * LEN);
-            double2 v[NJ];
-            double nrm = 0.0;
+    for (int side = 0; side < 2; ++side) {
+        const int slot = rank * 2 * W + side * W + w;
+        const double2* col = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(side * W + w) * LEN);
+        double2 v[NJ];
+        double nrm = 0.0;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) { v[j] = col[lane + 32 * j]; nrm = fma(v[j].x, v[j].x, nrm); nrm = fma(v[j].y, v[j].y, nrm); }
+        for (int j = 0; j < NJ; ++j) { v[j] = col[lane + 32 * j]; nrm = fma(v[j].x, v[j].x, nrm); nrm = fma(v[j].y, v[j].y, nrm); }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-            nrm = sqrt(nrm);
-            const bool real_col = k < npairs && nrm > 0.0;
-            if (lane == 0) wtmp[slot] = real_col ? nrm - sigma : 1.0e308;      // padding columns sort last
-            const double inv = real_col ? 1.0 / nrm : 0.0;
+        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        nrm = sqrt(nrm);
+        const bool real_col = nrm > 0.0;
+        if (lane == 0) wtmp[slot] = real_col ? (factor_mode ? nrm * nrm : nrm - sigma) : 1.0e308;   // padding columns sort last
+        const double inv = real_col ? 1.0 / nrm : 0.0;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int r0 = 2 * (lane + 32 * j);
-                if (r0 < n) qtmp[(size_t)slot * LEN + r0] = v[j].x * inv;
-                if (r0 + 1 < n) qtmp[(size_t)slot * LEN + r0 + 1] = v[j].y * inv;
-            }
+        for (int j = 0; j < NJ; ++j) {
+            const int r0 = 2 * (lane + 32 * j);
+            if (r0 < n) qtmp[(size_t)slot * LEN + r0] = v[j].x * inv;
+            if (r0 + 1 < n) qtmp[(size_t)slot * LEN + r0 + 1] = v[j].y * inv;
         }
     }
     if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = converged; }
 }
 
-// ascending order: w[rank] = value, Q[r][rank] = qtmp[slot][r]
+// ascending order: w[rank] = value, Q[r][rank] = qtmp[slot][r]; every CTA ranks all slots, then scatters its share
 __global__ void __launch_bounds__(1024)
 jacobi_sort_kernel(const double* __restrict__ wtmp, const double* __restrict__ qtmp, int slots, int len, int n,
                    double* __restrict__ w, double* __restrict__ Q, int64_t ldq) {
@@ -215,27 +319,137 @@ jacobi_sort_kernel(const double* __restrict__ wtmp, const double* __restrict__ q
         int r = 0;
         for (int j = 0; j < slots; ++j) { const double u = wtmp[j]; r += (u < v) || (u == v && j < i); }
         s_rank[i] = r;
-        if (r < n) w[r] = v;
+        if (r < n && blockIdx.x == 0) w[r] = v;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < slots * n; e += blockDim.x) {
-        const int slot = e / n, r = e - slot * n;
-        const int c = s_rank[slot];
-        if (c < n) Q[(int64_t)r * ldq + c] = qtmp[(size_t)slot * len + r];
+    // 32 x 32 tiles through shared memory so that both the reads (along r) and the writes (along c) coalesce
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_r = (n + 31) / 32, tiles_s = (slots + 31) / 32;
+    for (int tIdx = blockIdx.x; tIdx < tiles_r * tiles_s; tIdx += gridDim.x) {
+        const int s0 = (tIdx / tiles_r) * 32, r0 = (tIdx % tiles_r) * 32;
+        __syncthreads();
+        if (s0 + ty < slots && r0 + tx < n) tile[ty][tx] = qtmp[(size_t)(s0 + ty) * len + r0 + tx];
+        __syncthreads();
+        // thread (ty, tx): row r0 + ty, slot s0 + tx -> column rank[slot]; ranks of neighbouring slots are not
+        // contiguous in general, but after convergence they mostly are (nearly sorted columns)
+        if (s0 + tx < slots && r0 + ty < n) {
+            const int c = s_rank[s0 + tx];
+            if (c < n) Q[(int64_t)(r0 + ty) * ldq + c] = tile[tx][ty];
+        }
     }
 }
 
+// ---- orders beyond the shared memory of a cluster (320 < n <= 1024): the whole GPU, cooperative launch ------
+// Same one-sided method; the columns stay in global memory (8 MB at n = 1000: L2 resident), one WARP per pair
+// with both columns in registers (NQ 16-byte chunks per lane and column), pairs chosen by the circle method on
+// INDICES (nothing moves), one grid barrier per round.  Per round every column is read and written once
+// (16 MB of L2 traffic at n = 1000) -- the barrier and the L2 round trip, ~3 us, are the cost.
+// bt: n x ldb, row c = column c of B (contiguous), rotated in place.
+template <int NQ>
+__global__ void __launch_bounds__(128)
+jacobi_grid_kernel(double* __restrict__ bt, int64_t ldb, int n, double tol, int* __restrict__ flags,
+                   int* __restrict__ info) {
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nw = (int)((gridDim.x * blockDim.x) >> 5);
+    const int P = (n + 1) & ~1, half = P / 2;
+    const double tol2 = tol * tol;
+    int sweep = 0, converged = 0;
+    for (; sweep < JC_MAX_SWEEPS; ++sweep) {
+        int rot = 0;
+        for (int t = 0; t < P - 1; ++t) {
+            for (int i = gw; i < half; i += nw) {
+                int a, b;
+                if (i == 0) { a = P - 1; b = t; } else { a = (t + i) % (P - 1); b = (t - i + P - 1) % (P - 1); }
+                if (a > b) { const int x = a; a = b; b = x; }
+                if (b >= n) continue;
+                double2* cp = reinterpret_cast<double2*>(bt + (int64_t)a * ldb);
+                double2* cq = reinterpret_cast<double2*>(bt + (int64_t)b * ldb);
+                double2 p[NQ], q[NQ];
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const int ch = lane + 32 * j;
+                    p[j] = make_double2(0.0, 0.0); q[j] = p[j];
+                    if (2 * ch < n) { p[j] = __ldcg(cp + ch); q[j] = __ldcg(cq + ch); }     // L2: written by other SMs last round
+                    alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
+                    beta = fma(q[j].x, q[j].x, beta); beta = fma(q[j].y, q[j].y, beta);
+                    gamma = fma(p[j].x, q[j].x, gamma); gamma = fma(p[j].y, q[j].y, gamma);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+                    beta += __shfl_xor_sync(0xffffffffu, beta, o);
+                    gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+                }
+                double c, s;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
+                    rot = 1;
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) {
+                        const int ch = lane + 32 * j;
+                        if (2 * ch < n) {
+                            double2 x, y;
+                            x.x = c * p[j].x - s * q[j].x; x.y = c * p[j].y - s * q[j].y;
+                            y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
+                            __stcg(cp + ch, x);
+                            __stcg(cq + ch, y);
+                        }
+                    }
+                }
+            }
+            if (t == P - 2 && rot && lane == 0) atomicOr(flags + sweep, 1);
+            grid.sync();
+        }
+        const int any = *reinterpret_cast<volatile int*>(flags + sweep);
+        if (!any) { converged = 1; ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = converged; }
+}
+
+// bt (n x ldb, ldb even, padding zeroed) <- columns of sym(G) + sigma I (mode 0) or rows of the factor U (mode 1)
+__global__ void jacobi_grid_init_kernel(const double* __restrict__ G, int64_t ldg, int n, int factor_mode,
+                                        const double* __restrict__ par, double* __restrict__ bt, int64_t ldb,
+                                        int* __restrict__ flags) {
+    const double sigma = factor_mode ? 0.0 : par[0];
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = threadIdx.x; i < JC_MAX_SWEEPS; i += blockDim.x) flags[i] = 0;
+    for (int c = blockIdx.y; c < n; c += gridDim.y)
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ldb; r += gridDim.x * blockDim.x) {
+            double v = 0.0;
+            if (r < n) v = factor_mode ? G[(int64_t)c * ldg + r]
+                                       : 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) + (r == c ? sigma : 0.0);
+            bt[(int64_t)c * ldb + r] = v;
+        }
+}
+
+// column norms -> eigenvalues, normalised columns in place; one warp per column
+__global__ void jacobi_grid_finish_kernel(double* __restrict__ bt, int64_t ldb, int n, int factor_mode,
+                                          const double* __restrict__ par, double* __restrict__ wtmp) {
+    const int lane = threadIdx.x & 31;
+    const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= n) return;
+    const double sigma = factor_mode ? 0.0 : par[0];
+    double* col = bt + (int64_t)c * ldb;
+    double nrm = 0.0;
+    for (int r = lane; r < n; r += 32) nrm = fma(col[r], col[r], nrm);
+    nrm = sqrt(warp_sum(nrm));
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int r = lane; r < n; r += 32) col[r] *= inv;
+    if (lane == 0) wtmp[c] = nrm > 0.0 ? (factor_mode ? nrm * nrm : nrm - sigma) : (factor_mode ? 0.0 : -sigma);
+}
+
 template <int NJ>
-static int launch_cluster(const double* G, int64_t ldg, int n, int npairs, int W, int csize, const double* par,
+static int launch_cluster(const double* G, int64_t ldg, int n, int W, int csize, int factor_mode, double tol, const double* par,
                           double* wtmp, double* qtmp, int* info, cudaStream_t st) {
     const size_t smem = (size_t)2 * 2 * W * 64 * NJ * sizeof(double);
     static size_t configured = 0;
-    static bool nonportable = false;
     if (smem > configured) {
         RL_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    (void)nonportable;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)csize);
     cfg.blockDim = dim3((unsigned)(W * 32));
@@ -249,7 +463,7 @@ static int launch_cluster(const double* G, int64_t ldg, int n, int npairs, int W
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ++g_launches;
-    return (int)cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<NJ>, G, ldg, n, npairs, W, par, wtmp, qtmp, info);
+    return (int)cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<NJ>, G, ldg, n, W, factor_mode, tol, par, wtmp, qtmp, info);
 }
 
 }  // namespace rl
@@ -259,27 +473,81 @@ using namespace rl;
 extern "C" {
 
 int rl_syevj_cluster_max_n(void) { return 320; }
+int rl_syevj_grid_max_n(void) { return 1024; }
 
-/* workspace: par (8 doubles) | wtmp (2*npairs_padded) | qtmp (slots * len) | info (4 ints) */
+/* workspace: par (8 doubles) | wtmp | qtmp (slots * len) | info (4 ints); grid path: bt (n * ldb) + flags */
 size_t rl_syevj_cluster_ws_bytes(int64_t n) {
     if (n <= 0) return 0;
     const int64_t len = (n + 63) / 64 * 64;
     const int64_t slots = 2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER;
-    return (size_t)(8 + slots + slots * len) * sizeof(double) + 64;
+    return (size_t)(8 + slots + slots * len) * sizeof(double) + 1024;
+}
+
+static int syevj_grid(const double* g, int64_t ldg, int64_t n, int factor_mode, double tol, double* w, double* q,
+                      int64_t ldq, void* ws, int* info, cudaStream_t st) {
+    const int64_t len = (n + 63) / 64 * 64;
+    double* par = (double*)ws;
+    double* wtmp = par + 8;
+    double* bt = wtmp + (2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER);
+    int* flags = (int*)(bt + (size_t)n * len);
+    if (!factor_mode) {
+        jacobi_shift_kernel<<<1, 1024, 0, st>>>(g, ldg, (int)n, par);
+        int rc = check_launch();
+        if (rc) return rc;
+    }
+    jacobi_grid_init_kernel<<<dim3((unsigned)((len + 127) / 128), (unsigned)(n > 65535 ? 65535 : n)), 128, 0, st>>>(
+        g, ldg, (int)n, factor_mode, par, bt, len, flags);
+    int rc = check_launch();
+    if (rc) return rc;
+    const int NQ = (int)(len / 64);
+    const int half = (int)((n + 1) / 2);
+    int want = (half + 3) / 4;                       // one warp per pair, 4 warps per CTA
+    void* kern = nullptr;
+    if (NQ <= 8) kern = (void*)jacobi_grid_kernel<8>; else kern = (void*)jacobi_grid_kernel<16>;
+    int per_sm = 0;
+    RL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    const int cap = per_sm * sm_count();
+    int grid = want < cap ? want : cap;
+    if (grid < 1) grid = 1;
+    int ni = (int)n;
+    int64_t ldb = len;
+    void* args[] = {&bt, &ldb, &ni, &tol, &flags, &info};
+    rc = (int)cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(128), args, 0, st);
+    ++g_launches;
+    if (rc) return rc;
+    jacobi_grid_finish_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(bt, len, (int)n, factor_mode, par, wtmp);
+    rc = check_launch();
+    if (rc) return rc;
+    jacobi_sort_kernel<<<(unsigned)(n >= 512 ? 64 : 8), 1024, (size_t)n * sizeof(int), st>>>(wtmp, bt, (int)n, (int)len, (int)n, w, q, ldq);
+    return check_launch();
 }
 
 /* Eigen-decomposition of the symmetric n x n fp64 matrix g (row-major, ldg; both triangles are
  * read and averaged): w[0..n) ascending, q[i*ldq + j] = component i of eigenvector j.
- * g is not modified.  info_d (device, 2 ints): sweeps, converged.  n <= rl_syevj_cluster_max_n(). */
-int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq, void* ws,
-                     size_t ws_bytes, int* info_d, void* stream) {
-    if (n < 0 || n > rl_syevj_cluster_max_n()) return RL_E_ARG;
+ * factor_mode != 0: g holds instead the UPPER Cholesky factor U of the matrix to decompose
+ * (U^T U = q diag(w) q^T): the rotations act on the rows of U, no shift is needed and every
+ * eigenvalue keeps its relative accuracy (Jacobi on the Cholesky factor, Veselic-Hari).
+ * tol: a column pair is rotated while |<p, q>| > tol |p| |q| (<= 0: sqrt(n) eps, working precision; the
+ * Rayleigh-Ritz step of fp32 problems stops at 1e-9).
+ * g is not modified.  info_d (device, 2 ints): sweeps, converged.  n <= rl_syevj_grid_max_n();
+ * orders up to rl_syevj_cluster_max_n() run on one thread-block cluster, larger ones on the whole GPU. */
+int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, int factor_mode, double tol, double* w, double* q,
+                     int64_t ldq, void* ws, size_t ws_bytes, int* info_d, void* stream) {
+    if (n < 0 || n > rl_syevj_grid_max_n()) return RL_E_ARG;
     if (n == 0) return 0;
+    if (!(tol > 0.0)) tol = sqrt((double)n) * 2.220446049250313e-16;      // default: working precision
     if (ws_bytes < rl_syevj_cluster_ws_bytes(n)) return RL_E_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     const int npairs = (int)((n + 1) / 2);
     const int NJ = (int)((n + 63) / 64);
     const int len = 64 * NJ;
+    double* par = (double*)ws;
+    double* wtmp = par + 8;
+    double* qtmp = wtmp + (size_t)(2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER);
+    int* info_ws = (int*)(qtmp + (size_t)(2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER) * len);
+    int* info = info_d ? info_d : info_ws;
+    Span span(PK_SYEVJ, st, 2.0 * n * n * 8, 0.0);
+    if (n > rl_syevj_cluster_max_n()) return syevj_grid(g, ldg, n, factor_mode, tol, w, q, ldq, ws, info, st);
     // smallest cluster whose CTAs hold their pairs within 32 warps and the shared-memory budget
     // (<= 16 warps per CTA when possible: the FP64 pipe of one SM issues 2 warp-DFMAs per clock)
     int csize = 1, W = npairs;
@@ -291,26 +559,23 @@ int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, double* w, double*
         csize *= 2;
     }
     if (W < 1) W = 1;
-    double* par = (double*)ws;
-    double* wtmp = par + 8;
     const int slots = 2 * csize * W;
-    double* qtmp = wtmp + (size_t)(2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER);
-    int* info_ws = (int*)(qtmp + (size_t)(2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER) * len);
-    int* info = info_d ? info_d : info_ws;
-    Span span(PK_SYEVJ, st, 2.0 * n * n * 8, 0.0);
-    jacobi_shift_kernel<<<1, 1024, 0, st>>>(g, ldg, (int)n, par);
-    int rc = check_launch();
-    if (rc) return rc;
+    int rc = 0;
+    if (!factor_mode) {
+        jacobi_shift_kernel<<<1, 1024, 0, st>>>(g, ldg, (int)n, par);
+        rc = check_launch();
+        if (rc) return rc;
+    }
     switch (NJ) {
-        case 1: rc = launch_cluster<1>(g, ldg, (int)n, npairs, W, csize, par, wtmp, qtmp, info, st); break;
-        case 2: rc = launch_cluster<2>(g, ldg, (int)n, npairs, W, csize, par, wtmp, qtmp, info, st); break;
-        case 3: rc = launch_cluster<3>(g, ldg, (int)n, npairs, W, csize, par, wtmp, qtmp, info, st); break;
-        case 4: rc = launch_cluster<4>(g, ldg, (int)n, npairs, W, csize, par, wtmp, qtmp, info, st); break;
-        case 5: rc = launch_cluster<5>(g, ldg, (int)n, npairs, W, csize, par, wtmp, qtmp, info, st); break;
+        case 1: rc = launch_cluster<1>(g, ldg, (int)n, W, csize, factor_mode, tol, par, wtmp, qtmp, info, st); break;
+        case 2: rc = launch_cluster<2>(g, ldg, (int)n, W, csize, factor_mode, tol, par, wtmp, qtmp, info, st); break;
+        case 3: rc = launch_cluster<3>(g, ldg, (int)n, W, csize, factor_mode, tol, par, wtmp, qtmp, info, st); break;
+        case 4: rc = launch_cluster<4>(g, ldg, (int)n, W, csize, factor_mode, tol, par, wtmp, qtmp, info, st); break;
+        case 5: rc = launch_cluster<5>(g, ldg, (int)n, W, csize, factor_mode, tol, par, wtmp, qtmp, info, st); break;
         default: return RL_E_ARG;
     }
     if (rc) return rc;
-    jacobi_sort_kernel<<<1, 1024, (size_t)slots * sizeof(int), st>>>(wtmp, qtmp, slots, len, (int)n, w, q, ldq);
+    jacobi_sort_kernel<<<(unsigned)(n >= 128 ? 8 : 1), 1024, (size_t)slots * sizeof(int), st>>>(wtmp, qtmp, slots, len, (int)n, w, q, ldq);
     return check_launch();
 }
 

@@ -19,6 +19,17 @@
 
 namespace rl {
 
+// tcgen05 / TMEM / TMA GEMM of gemm_tc.cu (3xTF32, fp32 result)
+bool gemm_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx);
+int gemm_tc(const float* a_hi, const float* a_lo, int64_t lda, int64_t M, int64_t N, const float* x, int64_t ldx,
+            float* y, int64_t ldy, int64_t k, int transp, double alpha, double beta, void* ws, size_t ws_bytes,
+            cudaStream_t st);
+size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t k, int transp);
+
+// fp32 blocks with at least this many vectors on both sides go to the tensor cores: the Gram product and the
+// block update are then real contractions (32 flop/B at m = k = 128), not streaming kernels
+constexpr int64_t TC_BLOCK_MIN = 48;
+
 // ------------------------------------------------------------------ small helpers
 __global__ void small_copy_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst,
                                   int64_t ldd, int rows, int cols) {
@@ -451,10 +462,14 @@ piv_chol_kernel(double* __restrict__ A, double* __restrict__ A0, int64_t ld, int
         }
         if (tid == 0) A[(int64_t)i * ld + i] = r;
         __syncthreads();
-        const double* rowi = A + (int64_t)i * ld;
+        // row i staged in shared memory: the update's loads must not be ordered against its own stores
+        for (int c = i + 1 + tid; c < n; c += blockDim.x) vec[c] = A[(int64_t)i * ld + c];
+        __syncthreads();
         for (int rr = i + 1 + ty; rr < n; rr += 32) {
-            const double f = rowi[rr];
-            for (int cc = i + 1 + tx; cc < n; cc += 32) A[(int64_t)rr * ld + cc] = fma(-f, rowi[cc], A[(int64_t)rr * ld + cc]);
+            const double f = vec[rr];
+            double* row = A + (int64_t)rr * ld;
+#pragma unroll 4
+            for (int cc = i + 1 + tx; cc < n; cc += 32) row[cc] = fma(-f, vec[cc], row[cc]);
         }
         __syncthreads();
         if (i >= k && (i - l == blk - 1 || i == n - 1)) {
@@ -489,6 +504,220 @@ piv_chol_kernel(double* __restrict__ A, double* __restrict__ A0, int64_t ld, int
     }
     __syncthreads();
     if (tid == 0) { info[0] = dropped; info[1] = status; info[2] = drop_case; info[3] = last_check; }
+}
+
+// ---- the same factorisation with the working tile in SHARED memory --------------------------------
+// The global-memory kernel above pays an L2 round trip per dependent step (measured: 2.8 ms at n = 256).
+// Split as the reference itself does (solver.py:1756-1762): (1) unpivoted Cholesky of the leading k x k
+// block in shared memory, (2) U12 = U11^-T A12 by the multi-CTA triangular solve, (3) A22 -= U12^T U12 by
+// the tiled GEMM, (4) pivoted factorisation of the (n-k) x (n-k) trailing block in shared memory, columns
+// of U12 swapped in global memory; the tile is flushed to global memory before every condition estimate.
+constexpr int CH_SMEM_MAX = 150;       // 150 x 151 doubles = 181 KB
+
+__global__ void __launch_bounds__(CH_THREADS)
+chol_lead_smem_kernel(double* __restrict__ A, double* __restrict__ A0, int64_t ld, int n, int k,
+                      int* __restrict__ ind, int* __restrict__ info) {
+    extern __shared__ double T[];                 // k x (k + 1)
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int lt = k + 1;
+    for (int i = tid; i < n; i += blockDim.x) ind[i] = i;
+    for (int r = ty; r < n; r += 32)
+        for (int c = tx; c < n; c += 32) {
+            const double v = A[(int64_t)r * ld + c];
+            A0[(int64_t)r * ld + c] = v;
+            if (r < k && c < k) T[r * lt + c] = v;
+        }
+    __syncthreads();
+    int status = 0, bad = k;
+    for (int i = 0; i < k; ++i) {
+        const double piv = T[i * lt + i];
+        if (!(piv > 0.0)) { status = 1; bad = i; break; }
+        const double r = sqrt(piv);
+        __syncthreads();
+        for (int c = i + 1 + tid; c < k; c += blockDim.x) T[i * lt + c] /= r;
+        if (tid == 0) T[i * lt + i] = r;
+        __syncthreads();
+        for (int rr = i + 1 + ty; rr < k; rr += 32) {
+            const double f = T[i * lt + rr];
+            for (int cc = i + 1 + tx; cc < k; cc += 32)
+                if (cc >= rr) T[rr * lt + cc] = fma(-f, T[i * lt + cc], T[rr * lt + cc]);
+        }
+        __syncthreads();
+    }
+    for (int r = ty; r < k; r += 32)
+        for (int c = tx; c < k; c += 32)
+            A[(int64_t)r * ld + c] = (c >= r && r < bad) ? T[r * lt + c] : 0.0;
+    // the block below U11 is zero in the factor (solver.py:1761)
+    for (int r = k + ty; r < n; r += 32)
+        for (int c = tx; c < k; c += 32) A[(int64_t)r * ld + c] = 0.0;
+    if (tid == 0) { info[0] = status ? n - bad : 0; info[1] = status; info[2] = status ? 2 : 0; info[3] = -1; }
+}
+
+__global__ void __launch_bounds__(CH_THREADS)
+chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int64_t ld, int n, int k, double eps,
+                      int* __restrict__ ind, int* __restrict__ info) {
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ double tile[32][33];
+    __shared__ double part[32];
+    __shared__ int s_j;
+    extern __shared__ double dyn[];               // vec (n) | T (ny x (ny + 1))
+    double* vec = dyn;
+    const int ny = n - k, lt = ny + 1;
+    double* T = dyn + ((n + 1) & ~1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = lane, ty = warp;
+    if (info[1] != 0) return;                     // the leading block was not positive definite
+    for (int r = ty; r < ny; r += 32)
+        for (int c = tx; c < ny; c += 32) T[r * lt + c] = A[(int64_t)(k + r) * ld + k + c];
+    __syncthreads();
+    int dropped = 0, drop_case = 0, last_check = -1, l = k;
+    const int blk = 64;
+    // rows [0, upto) of the tile -> global factor (upper part, zeros below the diagonal); always from row 0:
+    // later pivots swap columns of the rows factored earlier
+    auto flush = [&](int upto) {
+        for (int r = ty; r < upto; r += 32)
+            for (int c = tx; c < ny; c += 32)
+                A[(int64_t)(k + r) * ld + k + c] = c >= r ? T[r * lt + c] : 0.0;
+        __syncthreads();
+    };
+    for (int ii = 0; ii < ny; ++ii) {
+        const int i = k + ii;
+        double best = -1.0e308; int bj = ny;
+        for (int j = ii + tid; j < ny; j += blockDim.x) {
+            const double d = T[j * lt + j];
+            if (d > best) { best = d; bj = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+        if (lane == 0) { red[warp] = best; redi[warp] = bj; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; ++w)
+                if (red[w] > best || (red[w] == best && redi[w] < bj)) { best = red[w]; bj = redi[w]; }
+            s_j = bj;
+        }
+        __syncthreads();
+        const int j = s_j;
+        if (j != ii && j < ny) {
+            for (int c = tid; c < ny; c += blockDim.x) {
+                const double a = T[ii * lt + c];
+                T[ii * lt + c] = T[j * lt + c];
+                T[j * lt + c] = a;
+            }
+            for (int r = tid; r < k; r += blockDim.x) {          // the same two columns of U12
+                const double a = A[(int64_t)r * ld + k + ii];
+                A[(int64_t)r * ld + k + ii] = A[(int64_t)r * ld + k + j];
+                A[(int64_t)r * ld + k + j] = a;
+            }
+            __syncthreads();
+            for (int r = tid; r < ny; r += blockDim.x) {
+                const double a = T[r * lt + ii];
+                T[r * lt + ii] = T[r * lt + j];
+                T[r * lt + j] = a;
+            }
+            if (tid == 0) { const int t = ind[i]; ind[i] = ind[k + j]; ind[k + j] = t; }
+            __syncthreads();
+        }
+        const double piv = T[ii * lt + ii];
+        if (piv <= eps || !(piv > 0.0)) {
+            __syncthreads();
+            for (int r = ii + ty; r < ny; r += 32)
+                for (int c = tx; c < ny; c += 32) T[r * lt + c] = 0.0;
+            __syncthreads();
+            drop_case = 1;
+            dropped = n - i;
+            break;
+        }
+        const double r = sqrt(piv);
+        __syncthreads();
+        for (int c = ii + 1 + tid; c < ny; c += blockDim.x) {
+            T[ii * lt + c] /= r;
+            T[c * lt + ii] = 0.0;
+        }
+        if (tid == 0) T[ii * lt + ii] = r;
+        __syncthreads();
+        for (int rr = ii + 1 + ty; rr < ny; rr += 32) {
+            const double f = T[ii * lt + rr];
+            for (int cc = ii + 1 + tx; cc < ny; cc += 32) T[rr * lt + cc] = fma(-f, T[ii * lt + cc], T[rr * lt + cc]);
+        }
+        __syncthreads();
+        if (i - l == blk - 1 || i == n - 1) {
+            last_check = i;
+            flush(ii + 1);
+            const double ratio = cond_inverse(A, A0, ld, i + 1, ind, vec, tile, part, red);
+            if (ratio <= eps) {
+                __syncthreads();
+                for (int r = ii + ty; r < ny; r += 32)
+                    for (int c = tx; c < ny; c += 32) T[r * lt + c] = 0.0;
+                __syncthreads();
+                drop_case = 2;
+                dropped = n - i;
+                break;
+            }
+            if (i - l == blk - 1) l += blk;
+        }
+    }
+    __syncthreads();
+    flush(ny);
+    if (last_check < n - 1 && drop_case == 1) {
+        int i = last_check, j = n - dropped - 1;
+        while (i < j) {
+            const int mid = i + (j - i + 1) / 2;
+            const double ratio = cond_inverse(A, A0, ld, mid + 1, ind, vec, tile, part, red);
+            if (ratio <= eps) {
+                if (j > mid) { j = mid; continue; }
+                __syncthreads();
+                zero_rows(A, ld, n, j);
+                dropped = n - j;
+                break;
+            }
+            i = mid;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { info[0] = dropped; info[1] = 0; info[2] = drop_case; info[3] = last_check; }
+}
+
+// unpivoted Cholesky of one nb x nb diagonal block (nb <= 128) in shared memory, upper factor written back with
+// zeros below the diagonal; info[0] = 1 + global index of the first non-positive pivot (sticky)
+__global__ void __launch_bounds__(CH_THREADS)
+potrf_diag_kernel(double* __restrict__ A, int64_t ld, int j0, int nb, int* __restrict__ info) {
+    extern __shared__ double T[];                 // nb x (nb + 1)
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int lt = nb + 1;
+    if (info[0] != 0) return;
+    double* D = A + (int64_t)j0 * ld + j0;
+    for (int r = ty; r < nb; r += 32)
+        for (int c = tx; c < nb; c += 32) T[r * lt + c] = D[(int64_t)r * ld + c];
+    __syncthreads();
+    int bad = -1;
+    for (int i = 0; i < nb; ++i) {
+        const double piv = T[i * lt + i];
+        if (!(piv > 0.0)) { bad = i; break; }
+        const double rs = rsqrt(piv);
+        __syncthreads();
+        for (int c = i + 1 + tid; c < nb; c += blockDim.x) T[i * lt + c] *= rs;
+        if (tid == 0) T[i * lt + i] = piv * rs;
+        __syncthreads();
+        for (int rr = i + 1 + ty; rr < nb; rr += 32) {
+            const double f = T[i * lt + rr];
+            for (int cc = i + 1 + tx; cc < nb; cc += 32)
+                if (cc >= rr) T[rr * lt + cc] = fma(-f, T[i * lt + cc], T[rr * lt + cc]);
+        }
+        __syncthreads();
+    }
+    for (int r = ty; r < nb; r += 32)
+        for (int c = tx; c < nb; c += 32) D[(int64_t)r * ld + c] = c >= r ? T[r * lt + c] : 0.0;
+    if (bad >= 0 && tid == 0) info[0] = 1 + j0 + bad;
+}
+
+__global__ void zero_lower_kernel(double* __restrict__ A, int64_t ld, int n) {
+    for (int r = blockIdx.y; r < n; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < r; c += gridDim.x * blockDim.x)
+            A[(int64_t)r * ld + c] = 0.0;
 }
 
 // ------------------------------------------------------------------ triangular solves, many right-hand sides
@@ -620,6 +849,99 @@ __global__ void rr_select_kernel(const double* __restrict__ Q, int64_t ldq, cons
         }
 }
 
+// ------------------------------------------------------------------ small matrix <-> block of vectors
+// dst[r*ldd + c] = (T) src[r][c]  (or src[c][r] when trans): fp64 coefficients -> typed block
+template <typename T>
+__global__ void small_to_block_kernel(const double* __restrict__ src, int64_t lds, int rows, int cols, int trans,
+                                      T* __restrict__ dst, int64_t ldd) {
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+            dst[(int64_t)r * ldd + c] = (T)(trans ? src[(int64_t)c * lds + r] : src[(int64_t)r * lds + c]);
+}
+
+template <typename T>
+__global__ void block_to_small_kernel(const T* __restrict__ src, int64_t lds, int rows, int cols,
+                                      double* __restrict__ dst, int64_t ldd) {
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+            dst[(int64_t)r * ldd + c] = (double)src[(int64_t)r * lds + c];
+}
+
+// ------------------------------------------------------------------ partial SVD post-processing (partial_svd.py:163-235)
+// Gershgorin certificate for the diagonally scaled Gram matrix S = D^-1/2 G D^-1/2:
+// out[0] = max_i sum_{j != i} |S_ij|, out[1] = min_i G_ii, out[2] = max_i G_ii
+__global__ void __launch_bounds__(1024)
+psvd_gershgorin_kernel(const double* __restrict__ G, int64_t ld, int n, double* __restrict__ out) {
+    __shared__ double r0[32], r1[32], r2[32];
+    double rmax = 0.0, dmin = 1.0e308, dmax = -1.0e308;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+        const double di = G[(int64_t)i * ld + i];
+        double acc = 0.0;
+        for (int j = threadIdx.x & 31; j < n; j += 32)
+            if (j != i) acc += fabs(G[(int64_t)i * ld + j]) / sqrt(fabs(di * G[(int64_t)j * ld + j]));
+        acc = warp_sum(acc);
+        rmax = (acc > rmax || acc != acc) ? acc : rmax;
+        dmin = fmin(dmin, di);
+        dmax = fmax(dmax, di);
+    }
+    if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = rmax; r1[threadIdx.x >> 5] = dmin; r2[threadIdx.x >> 5] = dmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            rmax = (r0[w] > rmax || r0[w] != r0[w]) ? r0[w] : rmax;
+            dmin = fmin(dmin, r1[w]); dmax = fmax(dmax, r2[w]);
+        }
+        out[0] = rmax; out[1] = dmin; out[2] = dmax;
+    }
+}
+
+// S = D^-1/2 G D^-1/2
+__global__ void psvd_scale_kernel(const double* __restrict__ G, int64_t ld, int n, double* __restrict__ S, int64_t lds) {
+    for (int r = blockIdx.y; r < n; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+            S[(int64_t)r * lds + c] = G[(int64_t)r * ld + c] / sqrt(fabs(G[(int64_t)r * ld + r] * G[(int64_t)c * ld + c]));
+}
+
+__global__ void small_identity_kernel(double* __restrict__ a, int64_t ld, int n) {
+    for (int r = blockIdx.y; r < n; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+            a[(int64_t)r * ld + c] = r == c ? 1.0 : 0.0;
+}
+
+// out[0] = sum_ij g_ii uinv_ij^2 (squared Frobenius norm of D^1/2 U^-1); one CTA, fixed summation order
+__global__ void __launch_bounds__(1024)
+psvd_invbound_kernel(const double* __restrict__ uinv, int64_t ldu, const double* __restrict__ g, int64_t ldg, int n,
+                     double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int r = threadIdx.x >> 5; r < n; r += 32) {
+        const double d = g[(int64_t)r * ldg + r];
+        double s = 0.0;
+        for (int c = threadIdx.x & 31; c < n; c += 32) { const double v = uinv[(int64_t)r * ldu + c]; s = fma(v, v, s); }
+        acc = fma(d, s, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 32; ++w) t += red[w]; out[0] = t; }
+}
+
+// eigenpairs ascending (w, Q) -> descending singular values and the two coefficient matrices:
+// q[:, c] = Q[:, n-1-c];  cs[:, c] = q[:, c] / sigma[c] (0 where sigma == 0);  sigma[c] = sqrt(max(w[n-1-c], 0))
+__global__ void psvd_coeffs_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ w, int n,
+                                   double* __restrict__ q, double* __restrict__ cs, int64_t ldo,
+                                   double* __restrict__ sigma) {
+    for (int r = blockIdx.y; r < n; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+            const double lam = w[n - 1 - c];
+            const double sg = lam > 0.0 ? sqrt(lam) : 0.0;
+            const double v = Q[(int64_t)r * ldq + (n - 1 - c)];
+            q[(int64_t)r * ldo + c] = v;
+            cs[(int64_t)r * ldo + c] = sg > 0.0 ? v / sg : 0.0;
+            if (r == 0) sigma[c] = sg;
+        }
+}
+
 }  // namespace rl
 
 using namespace rl;
@@ -677,6 +999,24 @@ int rl_gram_dev(int dtype, const void* s, int64_t lds, int64_t m, const void* o,
                 int64_t n, double* out, int64_t ldout, void* stream) {
     if (m < 0 || k < 0 || n < 0) return RL_E_ARG;
     if (m == 0 || k == 0) return 0;
+    if (dtype == RL_F32 && m >= TC_BLOCK_MIN && k >= TC_BLOCK_MIN && n >= 1024 && g_knob[KNOB_BLOCK_TC] >= 0 &&
+        gemm_tc_supported(s, lds, o, ldo)) {
+        // G (k x m) = O (k x n) . S^T: the dense-apply kernel with the block S as the data matrix, n as the
+        // reduction dimension (split over the SMs, partial tiles reduced in a fixed order)
+        const size_t wsb = (gemm_tc_ws_bytes(m, n, k, 0) + 255) & ~size_t(255);
+        const int64_t ldt = (m + 3) / 4 * 4;
+        void* base = nullptr;
+        int rc = scratch_acquire(wsb + (size_t)k * ldt * sizeof(float), &base);
+        if (rc) return rc;
+        float* tmp = (float*)((char*)base + wsb);
+        {
+            Span span(PK_GRAM, as_stream(stream), (double)(s == o ? m : m + k) * n * 4.0 + (double)k * m * 8.0, 2.0 * n * m * k);
+            rc = gemm_tc((const float*)s, nullptr, lds, m, n, (const float*)o, ldo, tmp, ldt, k, 0, 1.0, 0.0, base, wsb,
+                         as_stream(stream));
+        }
+        if (rc) return rc;
+        return rl_block_to_small(RL_F32, tmp, ldt, k, m, out, ldout, stream);
+    }
     const size_t wsb = (rl_gram_acc64_ws_bytes(dtype, m, k, n) + 255) & ~size_t(255);
     void* base = nullptr;
     int rc = scratch_acquire(wsb + (size_t)k * m * sizeof(double), &base);
@@ -718,6 +1058,24 @@ int rl_update_dev(int dtype, void* out, int64_t ldo, int64_t m, const void* x, i
     if (m == 0 || n == 0) return 0;
     if (dtype == RL_F64 || k == 0) return rl_update(dtype, out, ldo, m, x, ldx, k, q, ldq, 1, alpha, beta, n, stream);
     if (dtype != RL_F32) return RL_E_DTYPE;
+    if (out == x) return RL_E_ALIAS;
+    if (m >= TC_BLOCK_MIN && k >= TC_BLOCK_MIN && n >= 1024 && g_knob[KNOB_BLOCK_TC] >= 0 && (ldo % 4 == 0) &&
+        host_aligned16(out)) {
+        // Out (m x n) = beta Out + alpha q^T (m x k) . X (k x n): dense apply, transposed form, X as the data matrix
+        const int64_t ldq32 = (k + 3) / 4 * 4;
+        const size_t wsb = (gemm_tc_ws_bytes(k, n, m, 1) + 255) & ~size_t(255);
+        void* base = nullptr;
+        int rc = scratch_acquire(wsb + (size_t)m * ldq32 * sizeof(float), &base);
+        if (rc) return rc;
+        float* qt = (float*)((char*)base + wsb);
+        if (gemm_tc_supported(x, ldx, qt, ldq32)) {
+            rc = rl_small_to_block(RL_F32, q, ldq, m, k, 1, qt, ldq32, stream);
+            if (rc) return rc;
+            Span span(PK_UPDATE, as_stream(stream), (1.0 * k + (beta != 0.0 ? 2.0 : 1.0) * m) * n * 4.0, 2.0 * n * k * m);
+            return gemm_tc((const float*)x, nullptr, ldx, k, n, qt, ldq32, (float*)out, ldo, m, 1, alpha, beta, base, wsb,
+                           as_stream(stream));
+        }
+    }
     void *pinned = nullptr, *dev = nullptr;
     int rc = staging_acquire((size_t)k * m * sizeof(float), &pinned, &dev);       // device half of the ring only
     if (rc) return rc;
@@ -777,8 +1135,32 @@ int rl_rr_conjugation(const double* zay, const double* zby, double* beta, int64_
 int rl_rr_piv_chol(double* a, double* a0, int64_t ld, int64_t n, int64_t k, double eps, int* ind, int* info,
                    void* stream) {
     if (n < 0 || k < 0 || k > n || n > 4096) return RL_E_ARG;
-    if (n == 0) return (int)cudaMemsetAsync(info, 0, 4 * sizeof(int), as_stream(stream));
-    piv_chol_kernel<<<1, CH_THREADS, (size_t)n * sizeof(double), as_stream(stream)>>>(a, a0, ld, (int)n, (int)k, eps, ind, info);
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) return (int)cudaMemsetAsync(info, 0, 4 * sizeof(int), st);
+    const int64_t ny = n - k;
+    if (k <= CH_SMEM_MAX && ny <= CH_SMEM_MAX && g_knob[KNOB_CHOL_GLOBAL] == 0) {
+        static bool configured = false;
+        if (!configured) {
+            const int cap = (int)((size_t)CH_SMEM_MAX * (CH_SMEM_MAX + 1) * sizeof(double) + 4096 * sizeof(double));
+            RL_CUDA(cudaFuncSetAttribute(chol_lead_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            RL_CUDA(cudaFuncSetAttribute(chol_tail_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            configured = true;
+        }
+        chol_lead_smem_kernel<<<1, CH_THREADS, (size_t)(k > 0 ? k * (k + 1) : 1) * sizeof(double), st>>>(a, a0, ld, (int)n, (int)k, ind, info);
+        int rc = check_launch();
+        if (rc) return rc;
+        if (ny == 0) return 0;
+        if (k > 0) {
+            rc = rl_small_trsm(0, a, ld, k, a + k, ld, ny, stream);                                   // U12 = U11^-T A12
+            if (rc) return rc;
+            rc = rl_small_gemm(1, 0, ny, ny, k, -1.0, a + k, ld, a + k, ld, 1.0, a + k * ld + k, ld, stream);   // A22 -= U12^T U12
+            if (rc) return rc;
+        }
+        const size_t smem = (size_t)(((n + 1) & ~int64_t(1)) + ny * (ny + 1)) * sizeof(double);
+        chol_tail_smem_kernel<<<1, CH_THREADS, smem, st>>>(a, a0, ld, (int)n, (int)k, eps, ind, info);
+        return check_launch();
+    }
+    piv_chol_kernel<<<1, CH_THREADS, (size_t)n * sizeof(double), st>>>(a, a0, ld, (int)n, (int)k, eps, ind, info);
     return check_launch();
 }
 
@@ -795,6 +1177,93 @@ int rl_rr_select(const double* q, int64_t ldq, const double* w, int64_t nxy, int
     if (nxy < 0 || leftXn < 0 || rightXn < 0 || leftXn + rightXn > nxy) return RL_E_ARG;
     if (nxy == 0) return 0;
     rr_select_kernel<<<small_grid((int)nxy, (int)nxy), 128, 0, as_stream(stream)>>>(q, ldq, w, (int)nxy, (int)leftXn, (int)rightXn, cx, ldcx, cz, ldcz, lmdx, lmdz);
+    return check_launch();
+}
+
+
+int rl_small_to_block(int dtype, const double* src, int64_t lds, int64_t rows, int64_t cols, int trans, void* dst,
+                      int64_t ldd, void* stream) {
+    if (rows < 0 || cols < 0) return RL_E_ARG;
+    if (rows == 0 || cols == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == RL_F32) small_to_block_kernel<float><<<small_grid((int)rows, (int)cols), 128, 0, st>>>(src, lds, (int)rows, (int)cols, trans, (float*)dst, ldd);
+    else if (dtype == RL_F64) small_to_block_kernel<double><<<small_grid((int)rows, (int)cols), 128, 0, st>>>(src, lds, (int)rows, (int)cols, trans, (double*)dst, ldd);
+    else return RL_E_DTYPE;
+    return check_launch();
+}
+
+int rl_block_to_small(int dtype, const void* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd,
+                      void* stream) {
+    if (rows < 0 || cols < 0) return RL_E_ARG;
+    if (rows == 0 || cols == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == RL_F32) block_to_small_kernel<float><<<small_grid((int)rows, (int)cols), 128, 0, st>>>((const float*)src, lds, (int)rows, (int)cols, dst, ldd);
+    else if (dtype == RL_F64) block_to_small_kernel<double><<<small_grid((int)rows, (int)cols), 128, 0, st>>>((const double*)src, lds, (int)rows, (int)cols, dst, ldd);
+    else return RL_E_DTYPE;
+    return check_launch();
+}
+
+int rl_psvd_gershgorin(const double* g, int64_t ld, int64_t n, double* out3, void* stream) {
+    if (n <= 0) return RL_E_ARG;
+    psvd_gershgorin_kernel<<<1, 1024, 0, as_stream(stream)>>>(g, ld, (int)n, out3);
+    return check_launch();
+}
+
+int rl_psvd_scale(const double* g, int64_t ld, int64_t n, double* s, int64_t lds, void* stream) {
+    if (n <= 0) return RL_E_ARG;
+    psvd_scale_kernel<<<small_grid((int)n, (int)n), 128, 0, as_stream(stream)>>>(g, ld, (int)n, s, lds);
+    return check_launch();
+}
+
+int rl_psvd_coeffs(const double* qin, int64_t ldq, const double* w, int64_t n, double* q, double* cs, int64_t ldo,
+                   double* sigma, void* stream) {
+    if (n <= 0) return RL_E_ARG;
+    psvd_coeffs_kernel<<<small_grid((int)n, (int)n), 128, 0, as_stream(stream)>>>(qin, ldq, w, (int)n, q, cs, ldo, sigma);
+    return check_launch();
+}
+
+
+int rl_small_potrf(double* a, int64_t ld, int64_t n, int* info_d, void* stream) {
+    if (n < 0 || !info_d) return RL_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    RL_CUDA(cudaMemsetAsync(info_d, 0, sizeof(int), st));
+    if (n == 0) return 0;
+    const int64_t NB = 128;
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * sizeof(double))));
+        configured = true;
+    }
+    for (int64_t j0 = 0; j0 < n; j0 += NB) {
+        const int64_t nb = n - j0 < NB ? n - j0 : NB;
+        const int64_t rest = n - j0 - nb;
+        potrf_diag_kernel<<<1, CH_THREADS, (size_t)(nb * (nb + 1)) * sizeof(double), st>>>(a, ld, (int)j0, (int)nb, info_d);
+        int rc = check_launch();
+        if (rc) return rc;
+        if (rest > 0) {
+            double* d = a + j0 * ld + j0;
+            rc = rl_small_trsm(0, d, ld, nb, d + nb, ld, rest, stream);                                  // U12 = U11^-T A12
+            if (rc) return rc;
+            rc = rl_small_gemm(1, 0, rest, rest, nb, -1.0, d + nb, ld, d + nb, ld, 1.0, d + nb * ld + nb, ld, stream);
+            if (rc) return rc;
+        }
+    }
+    zero_lower_kernel<<<small_grid((int)n, (int)n), 128, 0, st>>>(a, ld, (int)n);
+    return check_launch();
+}
+
+
+int rl_small_set_identity(double* a, int64_t ld, int64_t n, void* stream) {
+    if (n < 0) return RL_E_ARG;
+    if (n == 0) return 0;
+    small_identity_kernel<<<small_grid((int)n, (int)n), 128, 0, as_stream(stream)>>>(a, ld, (int)n);
+    return check_launch();
+}
+
+int rl_psvd_invbound(const double* uinv, int64_t ldu, const double* g, int64_t ldg, int64_t n, double* out,
+                     void* stream) {
+    if (n <= 0) return RL_E_ARG;
+    psvd_invbound_kernel<<<1, 1024, 0, as_stream(stream)>>>(uinv, ldu, g, ldg, (int)n, out);
     return check_launch();
 }
 

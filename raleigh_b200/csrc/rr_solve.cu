@@ -24,7 +24,8 @@ int rl_rr_select(const double*, int64_t, const double*, int64_t, int64_t, int64_
                  int64_t, double*, double*, void*);
 int rl_syevj_cluster_max_n(void);
 size_t rl_syevj_cluster_ws_bytes(int64_t);
-int rl_syevj_cluster(const double*, int64_t, int64_t, double*, double*, int64_t, void*, size_t, int*, void*);
+int rl_syevj_cluster(const double*, int64_t, int64_t, int, double, double*, double*, int64_t, void*, size_t, int*, void*);
+int rl_syevj_grid_max_n(void);
 }
 
 namespace rl {
@@ -40,10 +41,11 @@ static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 
 // eigen-decomposition of sym(G) (n x n, ldg): w ascending, eigenvectors as columns of Q (ldq)
 static int small_eigh(const double* G, int64_t ldg, int64_t n, double* w, double* Q, int64_t ldq, void* ws,
-                      size_t ws_bytes, int* info_d, cudaStream_t st) {
+                      size_t ws_bytes, int* info_d, cudaStream_t st, int factor_mode = 0, double tol = 0.0) {
     if (n == 0) return 0;
-    if (n <= rl_syevj_cluster_max_n() && g_knob[KNOB_EIG_LEGACY] == 0)
-        return rl_syevj_cluster(G, ldg, n, w, Q, ldq, ws, ws_bytes, info_d, st);
+    if (n <= rl_syevj_grid_max_n() && (g_knob[KNOB_EIG_LEGACY] == 0 || factor_mode))
+        return rl_syevj_cluster(G, ldg, n, factor_mode, tol, w, Q, ldq, ws, ws_bytes, info_d, st);
+    if (factor_mode) return RL_E_ARG;
     // large blocks: cooperative-grid two-sided kernel (small.cu) on a contiguous copy
     double* a = (double*)ws;
     const size_t off = align256((size_t)n * n * sizeof(double));
@@ -58,7 +60,7 @@ static int small_eigh(const double* G, int64_t ldg, int64_t n, double* w, double
 }
 
 static size_t eigh_ws_bytes(int64_t n) {
-    size_t a = rl_syevj_cluster_ws_bytes(n <= rl_syevj_cluster_max_n() ? n : rl_syevj_cluster_max_n());
+    size_t a = rl_syevj_cluster_ws_bytes(n <= rl_syevj_grid_max_n() ? n : rl_syevj_grid_max_n());
     size_t b = align256((size_t)n * n * sizeof(double)) + rl_syevj_ws_bytes(n);
     return a > b ? a : b;
 }
@@ -79,6 +81,15 @@ int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double* w, double* q,
     return small_eigh(g, ldg, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream));
 }
 
+/* w, Q = eigh(u^T u) from the upper Cholesky factor u (Jacobi on the factor: relative accuracy for every
+ * eigenvalue); n <= rl_syevj_grid_max_n() */
+int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double* w, double* q, int64_t ldq, void* ws,
+                         size_t ws_bytes, int* info_d, void* stream) {
+    if (n < 0 || n > rl_syevj_grid_max_n()) return RL_E_ARG;
+    if (ws_bytes < rl_small_eigh_ws_bytes(n)) return RL_E_WORKSPACE;
+    return small_eigh(u, ldu, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream), 1);
+}
+
 size_t rl_rr_solve_ws_bytes(int64_t nmax) {
     if (nmax <= 0) return 0;
     // W1, G, Q, Qy, T (n x n each) | w, wy (n each) | eigensolver workspace
@@ -88,11 +99,12 @@ size_t rl_rr_solve_ws_bytes(int64_t nmax) {
 
 /* ga: (nxy x nxy) A-Gram matrix of (X, Y), full symmetric; u: upper Cholesky factor of their B-Gram
  * matrix (rl_rr_piv_chol), both with leading dimension ld.  Outputs: cx (nxy x nxn), cz (nxy x nz),
- * lmdx (nxn), lmdz (nz), est = dX (nx) followed by dlmd at est + nmax.  All device memory. */
+ * lmdx (nxn), lmdz (nz), est = dX (nx) followed by dlmd at est + nmax.  All device memory.
+ * eig_tol: stopping tolerance of the Jacobi eigensolver (<= 0: working precision). */
 int rl_rr_solve(const double* ga, const double* u, int64_t ld, int64_t nx, int64_t ny, int64_t leftX,
                 int64_t rightX, int64_t leftXn, int64_t rightXn, double* cx, int64_t ldcx, double* cz,
-                int64_t ldcz, double* lmdx, double* lmdz, double* est, int64_t nmax, void* ws, size_t ws_bytes,
-                int* info_d, void* stream) {
+                int64_t ldcz, double* lmdx, double* lmdz, double* est, int64_t nmax, double eig_tol, void* ws,
+                size_t ws_bytes, int* info_d, void* stream) {
     const int64_t n = nx + ny;
     if (nx < 0 || ny < 0 || n > nmax || leftX + rightX != nx || leftXn + rightXn > n) return RL_E_ARG;
     if (n == 0) return 0;
@@ -118,18 +130,18 @@ int rl_rr_solve(const double* ga, const double* u, int64_t ld, int64_t nx, int64
     RL_TRY(rl_small_trsm(0, u, ld, n, G, n, n, st));
     if (ny > 0 && nx > 0) {
         // rotate the Y block to the eigenbasis of its own Rayleigh-Ritz problem
-        RL_TRY(small_eigh(G + nx * n + nx, n, ny, wy, Qy, ny, ews, ews_bytes, nullptr, st));
+        RL_TRY(small_eigh(G + nx * n + nx, n, ny, wy, Qy, ny, ews, ews_bytes, nullptr, st, 0, eig_tol));
         RL_TRY(rl_small_gemm(0, 0, nx, ny, ny, 1.0, G + nx, n, Qy, ny, 0.0, T, ny, st));          // G[:nx, nx:] Qy
         RL_TRY(rl_small_copy(T, ny, G + nx, n, nx, ny, st));
         RL_TRY(rl_small_gemm(0, 0, ny, ny, ny, 1.0, G + nx * n + nx, n, Qy, ny, 0.0, T, ny, st)); // Gyy Qy
         RL_TRY(rl_small_gemm(1, 0, ny, ny, ny, 1.0, Qy, ny, T, ny, 0.0, G + nx * n + nx, n, st)); // Qy^T (Gyy Qy)
         RL_TRY(rl_small_mirror(G, n, nx, ny, st));
     } else if (ny > 0) {
-        RL_TRY(small_eigh(G, n, ny, wy, Qy, ny, ews, ews_bytes, nullptr, st));
+        RL_TRY(small_eigh(G, n, ny, wy, Qy, ny, ews, ews_bytes, nullptr, st, 0, eig_tol));
         RL_TRY(rl_small_gemm(0, 0, ny, ny, ny, 1.0, G, n, Qy, ny, 0.0, T, ny, st));
         RL_TRY(rl_small_gemm(1, 0, ny, ny, ny, 1.0, Qy, ny, T, ny, 0.0, G, n, st));
     }
-    RL_TRY(small_eigh(G, n, n, w, Q, n, ews, ews_bytes, info_d, st));
+    RL_TRY(small_eigh(G, n, n, w, Q, n, ews, ews_bytes, info_d, st, 0, eig_tol));
     if (nx > 0) RL_TRY(rl_rr_estimates(Q, n, w, nx, ny, leftX, rightX, est, est + nmax, st));
     if (ny > 0) {
         RL_TRY(rl_small_gemm(0, 0, ny, n, ny, 1.0, Qy, ny, Q + nx * n, n, 0.0, T, n, st));        // Qy Q[nx:, :]

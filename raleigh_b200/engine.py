@@ -52,6 +52,9 @@ class DeviceEngine:
         self.m = m
         self._template = vector
         self._code = vector._code
+        # Jacobi stopping tolerance of the Rayleigh-Ritz eigenproblems: working precision for fp64 data; for
+        # fp32 data the Gram matrices themselves carry 1e-7 relative noise
+        self._eig_tol = 1e-9 if vector._code == _lib.RL_F32 else 0.0
         M = 2 * m
         self.M = M
         rr_ws = lib.rl_rr_solve_ws_bytes(M)
@@ -225,7 +228,8 @@ class DeviceEngine:
     def _rr(self, nx, ny, leftX, rightX, leftXn, rightXn):
         check(lib.rl_rr_solve(self.GA.ptr, self.GB.ptr, self.GA.ld, nx, ny, leftX, rightX, leftXn, rightXn,
                               self.CX.ptr, self.CX.ld, self.CZ.ptr, self.CZ.ld, self._lmdx, self._lmdz,
-                              self._est_ptr, self.M, self._rr_ws, self._rr_ws_bytes, self._eig_info, dev.stream()))
+                              self._est_ptr, self.M, self._eig_tol, self._rr_ws, self._rr_ws_bytes, self._eig_info,
+                              dev.stream()))
 
     def fetch_estimates(self, nx):
         h, M = self._h_est, self.M

@@ -33,6 +33,23 @@ def _np_type(t):
     return numpy.dtype(t).type
 
 
+TC_MIN_VECTORS = 8                # below this the FMA-pipe / GEMV kernels are used
+
+
+def block_gemm(code, a_ptr, lda, M, N, x_ptr, ldx, y_ptr, ldy, k, transp, alpha=1.0, beta=0.0):
+    """Y = alpha X A^T (transp = 0) or alpha X A (transp = 1) + beta Y with A an (M, N) row-major block:
+    tcgen05 tensor cores (3xTF32, low parts split in shared memory) for fp32 whenever the operands
+    are TMA addressable, the FMA-pipe kernel otherwise."""
+    if (code == _lib.RL_F32 and k >= TC_MIN_VECTORS and
+            lib.rl_dense_apply_tc_supported(a_ptr, lda, x_ptr, ldx)):
+        wsb = lib.rl_dense_apply_tc_ws_bytes(M, N, k, transp)
+        ws = dev.Buffer(wsb)
+        check(lib.rl_dense_apply_tc(a_ptr, 0, lda, M, N, x_ptr, ldx, y_ptr, ldy, k, transp, alpha, beta, ws.ptr, wsb,
+                                    dev.stream()))
+        return
+    check(lib.rl_dense_apply(code, a_ptr, lda, M, N, x_ptr, ldx, y_ptr, ldy, k, transp, alpha, beta, dev.stream()))
+
+
 class Vectors:
     """Block of vectors resident in HBM.  dense_cublas.py:17-632."""
 
@@ -377,8 +394,7 @@ class Vectors:
         # q (k, m) = other (k, n) . self^T  == Matrix(self).apply(other)
         m, k = self.nvec(), other.nvec()
         q = Vectors._local(m, k, self._dtype)
-        check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, self._n, other._wptr(), other._ld,
-                                 q._wptr(), q._ld, k, 0, 1.0, 0.0, dev.stream()))
+        block_gemm(self._code, self._wptr(), self._ld, m, self._n, other._wptr(), other._ld, q._wptr(), q._ld, k, 0)
         return q.data()
 
     def _q_host(self, q, rows, cols):
@@ -405,8 +421,8 @@ class Vectors:
         if k > Vectors._GEMM_THRESHOLD:
             # self is a data matrix viewed as vectors (lra.py:236): out (m, n) = q^T (m, k) . S (k, n)
             qt = Vectors(numpy.ascontiguousarray(qh.T))
-            check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, k, self._n, qt._wptr(), qt._ld,
-                                     output._wptr(), output._ld, m, 1, 1.0, 0.0, dev.stream()))
+            block_gemm(self._code, self._wptr(), self._ld, k, self._n, qt._wptr(), qt._ld, output._wptr(),
+                       output._ld, m, 1)
             return
         check(lib.rl_update_h(self._code, output._wptr(), output._ld, m, self._wptr(), self._ld, k,
                               dev.host_ptr(qh), rs, cs, 1.0, 0.0, self._n, dev.stream()))
@@ -518,8 +534,7 @@ class Vectors:
         self._touch()
         if max(m, k) > Vectors._GEMM_THRESHOLD:
             # self is a data chunk: both products are real GEMMs
-            check(lib.rl_dense_apply(self._code, self._wptr(), self._ld, m, n, other._wptr(), other._ld,
-                                     q._wptr(), q._ld, k, 0, 1.0, 0.0, st))
+            block_gemm(self._code, self._wptr(), self._ld, m, n, other._wptr(), other._ld, q._wptr(), q._ld, k, 0)
         else:
             wsb = lib.rl_gram_ws_bytes(self._code, m, k, n)
             ws = dev.Buffer(wsb) if wsb else None
@@ -602,7 +617,8 @@ class Matrix:
         self._lo = None               # low part of the 3xTF32 split (tensor-core path)
         self._lo_version = -1
 
-    TC_MIN_VECTORS = 8                # below this the FMA-pipe kernel is used
+    TC_MIN_VECTORS = TC_MIN_VECTORS
+    MATERIALISED_LO = False           # True: keep a - tf32(a) in HBM (r1 scheme, twice the traffic; measurements only)
 
     def minmax(self):
         """(min, max) over the stored block in one HBM-bound pass on the device."""
@@ -706,12 +722,11 @@ class Matrix:
             self._mshard[0].allreduce_(view)
 
     def _apply_local(self, x, y, k, M, N, t):
-        if (self._dtype is numpy.float32 and k >= Matrix.TC_MIN_VECTORS and
-                lib.rl_dense_apply_tc_supported(self._aptr(), self._ld, x._wptr(), x._ld)):
-            wsb = lib.rl_dense_apply_tc_ws_bytes(M, N, k, t)
+        if Matrix.MATERIALISED_LO and self._dtype is numpy.float32 and k >= TC_MIN_VECTORS and \
+                lib.rl_dense_apply_tc_supported(self._aptr(), self._ld, x._wptr(), x._ld):
+            wsb = lib.rl_dense_apply_tc_ws_bytes(M, N, k, t)      # A/B variant: lo copy of the matrix in HBM
             ws = dev.Buffer(wsb)
             check(lib.rl_dense_apply_tc(self._aptr(), self._lo_ptr(), self._ld, M, N, x._wptr(), x._ld,
                                         y._wptr(), y._ld, k, t, 1.0, 0.0, ws.ptr, wsb, dev.stream()))
             return
-        check(lib.rl_dense_apply(self._code, self._aptr(), self._ld, M, N, x._wptr(), x._ld, y._wptr(), y._ld,
-                                 k, t, 1.0, 0.0, dev.stream()))
+        block_gemm(self._code, self._aptr(), self._ld, M, N, x._wptr(), x._ld, y._wptr(), y._ld, k, t)

@@ -136,8 +136,12 @@ def _eig(rt, G, fn='rl_syevj_cluster'):
     wsb = rt.lib.rl_small_eigh_ws_bytes(n)
     ws = rt.zeros(wsb // 8 + 8)
     info = rt.zeros(4, dtype=rt.torch.int32)
-    rt.check(getattr(rt.lib, fn)(dG.data_ptr(), ld, n, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
-                                 info.data_ptr(), rt.st()))
+    if fn == 'rl_syevj_cluster':
+        rt.check(rt.lib.rl_syevj_cluster(dG.data_ptr(), ld, n, 0, 0.0, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
+                                         info.data_ptr(), rt.st()))
+    else:
+        rt.check(getattr(rt.lib, fn)(dG.data_ptr(), ld, n, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
+                                     info.data_ptr(), rt.st()))
     return w.cpu().numpy(), Q.cpu().numpy(), info.cpu().numpy()
 
 
@@ -171,7 +175,45 @@ def test_cluster_jacobi_eigh(rt, n, kind):
         assert abs(int(info[0]) - sweeps) <= 1, (info, sweeps)
 
 
-@pytest.mark.parametrize('n', [8, 100, 340, 500])
+@pytest.mark.parametrize('n', [1, 7, 64, 130, 321, 500, 1000])
+@pytest.mark.parametrize('cond', [1e2, 1e8])
+def test_potrf_and_jacobi_on_the_factor(rt, n, cond):
+    """G = U^T U (blocked Cholesky on the device), then eigh from the factor: every eigenvalue to relative
+    accuracy even at condition 1e8 (the plain symmetric solver is only absolutely accurate)."""
+    rng = np.random.RandomState(n)
+    q, _ = np.linalg.qr(rng.randn(n, n))
+    lam = np.logspace(0, -np.log10(cond), n) if n > 1 else np.ones(1)
+    # graded matrix: well conditioned after diagonal scaling, like the Gram matrix of nearly singular vectors
+    d = np.sqrt(lam)
+    S = np.eye(n) + 1e-3 * (q + q.T)
+    G = d[:, None] * S * d[None, :]
+    dU = rt.up(G)
+    info = rt.zeros(4, dtype=rt.torch.int32)
+    rt.check(rt.lib.rl_small_potrf(dU.data_ptr(), n, n, info.data_ptr(), rt.st()))
+    assert int(info[0]) == 0
+    U = dU.cpu().numpy()
+    assert np.max(np.abs(np.tril(U, -1))) == 0.0
+    assert np.max(np.abs(U.T @ U - G) / np.sqrt(np.outer(np.diag(G), np.diag(G)))) < 1e-13 * max(n, 8)
+    w, Q = rt.zeros(n), rt.zeros(n, n)
+    wsb = rt.lib.rl_small_eigh_ws_bytes(n)
+    ws = rt.zeros(wsb // 8 + 8)
+    rt.check(rt.lib.rl_small_eigh_factor(dU.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
+                                         info.data_ptr(), rt.st()))
+    w, Q = w.cpu().numpy(), Q.cpu().numpy()
+    assert int(info[1]) == 1, info.cpu().numpy()
+    wr = np.linalg.eigvalsh(G.astype(np.longdouble).astype(np.float64))
+    # relative accuracy against the eigenvalues of the scaled problem solved in extended precision
+    Sr = np.linalg.eigvalsh(S)
+    assert np.all(w > 0)
+    assert np.max(np.abs(Q.T @ Q - np.eye(n))) < 1e-13 * max(n, 8)
+    resid = G @ Q - Q * w[None, :]
+    assert np.max(np.abs(resid) / d[:, None]) / np.max(d) < 1e-12 * max(n, 8)
+    if cond <= 1e2:
+        assert np.max(np.abs(w - wr) / wr) < 1e-12 * max(n, 8)
+    assert Sr[0] > 0
+
+
+@pytest.mark.parametrize('n', [8, 100, 340, 500, 1024, 1100])
 def test_small_eigh_dispatch(rt, n):
     rng = np.random.RandomState(n)
     G = rng.randn(n, n); G = G + G.T
@@ -217,7 +259,7 @@ def test_rr_solve_against_lapack(rt, nx, ny, lx, rx, lxn, rxn):
     ws = rt.zeros(wsb // 8 + 8)
     info = rt.zeros(4, dtype=rt.torch.int32)
     rt.check(rt.lib.rl_rr_solve(dGA.data_ptr(), dU.data_ptr(), ld, nx, ny, lx, rx, lxn, rxn, cx.data_ptr(), n,
-                                cz.data_ptr(), n, lmdx.data_ptr(), lmdz.data_ptr(), est.data_ptr(), n, ws.data_ptr(),
+                                cz.data_ptr(), n, lmdx.data_ptr(), lmdz.data_ptr(), est.data_ptr(), n, 0.0, ws.data_ptr(),
                                 wsb, info.data_ptr(), rt.st()))
     nxn, nz = lxn + rxn, n - lxn - rxn
     lx_d, lz_d = lmdx.cpu().numpy()[:nxn], lmdz.cpu().numpy()[:nz]

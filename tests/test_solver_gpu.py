@@ -232,3 +232,69 @@ def test_device_solver_pca_matches_verbatim(gpu_backend, ref):
     e0, e1 = pca_error(A, m0, t0, c0), pca_error(A, m1, t1, c1)
     assert abs(e0[0] - e1[0]) < 2e-3 and abs(e0[1] - e1[1]) < 2e-3
     assert np.max(np.abs(c1 @ c1.T - np.eye(300))) < 1e-3
+
+
+@pytest.mark.parametrize('dtype,nsv,cond', [(np.float32, 60, 1e2), (np.float32, 200, 1e3), (np.float64, 100, 1e5),
+                                            (np.float32, 1000, 2e2)])
+def test_device_finalize_svd_against_reference(gpu_backend, ref, dtype, nsv, cond):
+    """psvd.finalize_svd (one device eigen-decomposition) against the reference's
+    PartialSVD._finalize_svd (host cholesky / svd / inv, partial_svd.py:163-235) on the same inputs."""
+    from raleigh.interfaces.partial_svd import PartialSVD
+    from raleigh_b200 import psvd
+    rng = np.random.RandomState(nsv)
+    m, n = 3 * nsv + 17, 2 * nsv + 5
+    sig = np.logspace(0, -np.log10(cond), nsv)
+    ua, _ = np.linalg.qr(rng.randn(m, nsv))
+    va, _ = np.linalg.qr(rng.randn(n, nsv))
+    # v: slightly rotated right singular vectors (what the solver delivers at svtol), Av = A v
+    rot, _ = np.linalg.qr(np.eye(nsv) + 1e-3 * rng.randn(nsv, nsv))
+    v0 = (va @ rot).T.astype(dtype)                      # (nsv, n)
+    A = (ua * sig) @ va.T
+    av0 = (A @ v0.T.astype(np.float64)).T.astype(dtype)  # (nsv, m)
+    V, AV = gpu_backend.Vectors(v0.copy()), gpu_backend.Vectors(av0.copy())
+    u, sigma, v = psvd.finalize_svd(V, AV, 1e-3)
+    Vr, AVr = gpu_backend.Vectors(v0.copy()), gpu_backend.Vectors(av0.copy())
+    gpu_backend.use_device_solver(False)
+    try:
+        ur, sigr, vr = PartialSVD._finalize_svd(Vr, AVr, 1e-3)
+    finally:
+        gpu_backend.use_device_solver(True)
+    tol = 1e-5 if dtype is np.float32 else 1e-10
+    assert sigma.dtype == dtype
+    assert np.max(np.abs(sigma - sigr) / sigr) < tol * 20            # relative, down to the smallest one
+    assert np.max(np.abs(sigma.astype(np.float64) - sig) / sig) < (2e-4 if dtype is np.float32 else 1e-6)
+    U, Vv = u.data().astype(np.float64), v.data().astype(np.float64)
+    ortho = 2e-5 if dtype is np.float32 else 1e-11
+    Ur = ur.data().astype(np.float64)
+    ref_ortho = np.max(np.abs(Ur @ Ur.T - np.eye(nsv)))
+    assert np.max(np.abs(U @ U.T - np.eye(nsv))) < max(ortho * 10, 10 * ref_ortho)      # eps * cond for both routes
+    assert np.max(np.abs(Vv @ Vv.T - np.eye(nsv))) < ortho * 10
+    # A v' = u diag(sigma)
+    lhs = A @ Vv.T
+    rhs = U.T * sigma.astype(np.float64)[None, :]
+    assert np.max(np.abs(lhs - rhs)) < (5e-6 if dtype is np.float32 else 1e-10)
+
+
+def test_device_pca_wide_matrix_uses_finalize(gpu_backend, ref):
+    """m < n: pca() sets ortho = svtol and goes through _finalize_svd (pca.py:147-148) -- the config-2 route."""
+    from raleigh.interfaces.pca import pca, pca_error
+    from raleigh.examples.pca.generate_matrix import generate
+    np.random.seed(1)
+    A, sigma, u, v = generate(500, 900, 300, pca=True)
+
+    def run():
+        np.random.seed(1)
+        return pca(A, npc=60, arch='gpu!', opt=ref.Options())
+
+    (m0, t0, c0), (m1, t1, c1) = _both_paths(gpu_backend, run)
+    assert c0.shape == c1.shape
+    sv0, sv1 = np.linalg.norm(t0, axis=0), np.linalg.norm(t1, axis=0)
+    lead = slice(0, 30)
+    # two fp32 computations of the same quantities: north_star's 1e-5 plus their own rounding
+    assert np.max(np.abs(sv1[lead] - sv0[lead]) / sv0[lead]) < 2e-5
+    # and both sit on the exact singular values of the centred matrix to the solver's own tolerance (svtol)
+    exact = np.linalg.svd(A.astype(np.float64) - A.astype(np.float64).mean(axis=0), compute_uv=False)
+    assert np.max(np.abs(sv1[:10] - exact[:10]) / exact[:10]) < 1e-4
+    e0, e1 = pca_error(A, m0, t0, c0), pca_error(A, m1, t1, c1)
+    assert abs(e0[0] - e1[0]) < 2e-3 and abs(e0[1] - e1[1]) < 2e-3
+    assert np.max(np.abs(c1 @ c1.T - np.eye(c1.shape[0]))) < 1e-4

@@ -74,7 +74,7 @@ def main():
 
         def rr():
             check(lib.rl_rr_solve(dGA.data_ptr(), dGB.data_ptr(), n, m, m, m, 0, m, 0, cx.data_ptr(), n, cz.data_ptr(), n,
-                                  lx.data_ptr(), lz.data_ptr(), est.data_ptr(), n, ws.data_ptr(), wsb, info.data_ptr(), st()))
+                                  lx.data_ptr(), lz.data_ptr(), est.data_ptr(), n, 0.0, ws.data_ptr(), wsb, info.data_ptr(), st()))
         t_rr = timeit(rr)
         sweeps_rr = int(info[0])
         w, Q = torch.zeros(n, dtype=torch.float64, device='cuda'), torch.zeros(n, n, dtype=torch.float64, device='cuda')
@@ -95,6 +95,40 @@ def main():
         t_trsm = timeit(trsm)
         emit(block=m, nxy=n, piv_chol_ms=round(t_chol, 4), rr_solve_ms=round(t_rr, 4), rr_final_eigh_sweeps=sweeps_rr,
              trsm_ms=round(t_trsm, 4), **res)
+    big(emit)
+
+
+def big(emit):
+    """Orders of the partial-SVD post-processing (nsv = 1000 at config 2): blocked Cholesky and Jacobi on the
+    factor for a graded, nearly diagonal Gram matrix; symmetric mode for comparison."""
+    st = dev.stream
+    for n in (500, 1000):
+        rng = np.random.RandomState(n)
+        sig = np.arange(1, n + 1) ** -0.75
+        E = rng.randn(n, n) * 3e-4
+        S = np.eye(n) + E + E.T
+        G = up(sig[:, None] * S * sig[None, :])
+        U = torch.zeros_like(G)
+        info = torch.zeros(8, dtype=torch.int32, device='cuda')
+        w, Q = torch.zeros(n, dtype=torch.float64, device='cuda'), torch.zeros(n, n, dtype=torch.float64, device='cuda')
+        ewsb = lib.rl_small_eigh_ws_bytes(n)
+        ews = torch.zeros(ewsb // 8 + 8, dtype=torch.float64, device='cuda')
+
+        def potrf():
+            U.copy_(G)
+            check(lib.rl_small_potrf(U.data_ptr(), n, n, info.data_ptr(), st()))
+        t_potrf = timeit(potrf, 5)
+
+        def fac():
+            check(lib.rl_small_eigh_factor(U.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+        t_fac = timeit(fac, 3)
+        sw_fac = int(info[0])
+
+        def sym():
+            check(lib.rl_small_eigh(G.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+        t_sym = timeit(sym, 3)
+        emit(order=n, potrf_ms=round(t_potrf, 3), eigh_factor_ms=round(t_fac, 3), eigh_factor_sweeps=sw_fac,
+             eigh_sym_ms=round(t_sym, 3), eigh_sym_sweeps=int(info[0]))
 
 
 if __name__ == '__main__':
