@@ -3,28 +3,35 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (config.workload = "C2"): PCA / truncated SVD of a synthetic
-12,000 x 39,375 fp32 low-rank + noise matrix (LFW 175x225 shape), 1,000 principal
-components -- BASELINE.json configs[1], the configuration the reference's README
-quotes (27 s CPU / 12 s GPU).  One "step" = one complete solve: the reference's
-unmodified LowerRankApproximation.compute -> PartialSVD -> core block-JCG solver
-running on the raleigh_b200 Vectors/Matrix backend.
+Workload (config.workload = "C2"): PCA / truncated SVD of the synthetic 12,000 x 39,375 fp32 low-rank +
+noise matrix (LFW 175x225 shape), 1,000 principal components -- BASELINE.json configs[1], the configuration
+the reference's README quotes (27 s CPU / 12 s GPU).  At N = 1 the matrix is produced by the reference's
+OWN generator (examples/pca/generate_matrix.py:74-77 `generate(12000, 39375, 2000, alpha=0.75, pca=True)`
+plus the --ptb noise, :122-125, numpy.random.seed(1)) -- config 2 as written, identical in both arms.
+One "step" = one complete solve: the reference's unmodified LowerRankApproximation.compute -> PartialSVD
+on the raleigh_b200 backend, with the block Jacobi-CG iteration and the partial-SVD post-processing running
+device-resident (raleigh_b200/jcg.py, psvd.py).
 
-  value : seconds per solve with the data matrix already resident in HBM
-  e2e   : seconds per `pca(A_host, npc=1000, arch='gpu!')` call: host matrix in
-          pinned memory -> H2D inside the timed region, components/scores D2H
-  roofline : the dominant kernel (dense operator application), measured live
-          with CUDA events inside the C library over the timed region
-  cpu_baseline : the reference's own CPU path (dense_numpy on NumPy/OpenBLAS; MKL
-          is not installable here) on the box's host cores
+  value     seconds per solve with the data matrix already resident in HBM
+  e2e       seconds per `pca(A_host, npc=1000, arch='gpu!')` call: host matrix in pinned memory -> H2D inside the
+            timed region, components / scores D2H
+  roofline  the dominant kernel of the step (dense operator application), measured live with CUDA events inside
+            the C library over the timed region
+  cpu_baseline  the reference's own CPU path (dense_numpy on NumPy/OpenBLAS; MKL is not installable here) on the
+            box's host cores, in a child process that never imports the product; its singular values are
+            compared with the GPU arm's (max_rel_sv_diff)
+  c4        bounded BASELINE config 4 (256^3 Laplacian row-sharded over the N GPUs, fixed iteration count,
+            block 32 and 120): seconds per iteration, SpMM / Gram GB/s per rank, halo and all-reduce traffic
+  hbm_kernels  block SpMM and Gram bandwidth on the per-GPU block of config 4 (second half of BASELINE's metric)
 
---impl reference times only that CPU path and prints the same line.
+--impl reference times only the reference's CPU path (no product import, no GPU) and prints the same line.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,6 +41,7 @@ sys.path.insert(0, ROOT)
 M_ROWS, N_COLS, RANK_GEN, NPC = 12000, 39375, 2000, 1000
 METRIC = 'time to k eigenpairs (s)'
 BASELINE_PUBLISHED_S = 12.0      # README.md:33 "raleigh GPU" column, 1000 components (GPU model not stated)
+REFERENCE_BUDGET_S = 200.0       # the whole --impl reference run must end within a few minutes
 
 
 def parse():
@@ -46,17 +54,59 @@ def parse():
     ap.add_argument('--cols', type=int, default=N_COLS)
     ap.add_argument('--npc', type=int, default=NPC)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-c4', action='store_true', help='skip the bounded config-4 leg')
+    ap.add_argument('--c4-grid', type=int, default=256)
+    ap.add_argument('--c4-iters', type=int, default=10)
+    ap.add_argument('--sv-out', default=None, help='(reference arm) save the singular values of the last solve')
+    ap.add_argument('--full', action='store_true', help='(reference arm) always run the full workload')
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------- workload
-def generate_c2(rows, cols, rank, device, seed=1, world=1, shard=0):
-    """Synthetic data matrix in the style of the reference's generator
-    (examples/pca/generate_matrix.py:55-77 with pca=True, alpha=0.75, plus the
-    --ptb noise, :122-125): A = U diag(k^-0.75) V^T + noise, U[:, 0] = const.
-    With world > 1 this returns rows [shard*rows, (shard+1)*rows) of the
-    (world*rows) x cols matrix: V is common to all shards, U is drawn per shard
-    and scaled so that its columns stay (nearly) orthonormal globally."""
+def c2_cache_path(rows, cols):
+    return os.path.join(tempfile.gettempdir(), 'raleigh_b200_c2_%dx%d_seed1.npy' % (rows, cols))
+
+
+def c2_host_matrix(rows, cols, rank=RANK_GEN):
+    """Config 2 as written: the reference's own generator and noise recipe on the host.
+    Cached in the temporary directory so that the two arms of one round (and the cpu_baseline child) share
+    the ~10 s generation."""
+    import numpy as np
+    path = c2_cache_path(rows, cols)
+    if os.path.exists(path):
+        try:
+            a = np.load(path)
+            if a.shape == (rows, cols) and a.dtype == np.float32:
+                return a
+        except Exception:
+            pass
+    from tools import refenv
+    if refenv.load_reference() is None:
+        raise RuntimeError('reference package (baseline/_ref) not on this box')
+    from raleigh.examples.pca.generate_matrix import generate
+    np.random.seed(1)
+    a, sigma, u, v = generate(rows, cols, min(rank, rows, cols), dtype=np.float32, alpha=0.75, pca=True)
+    del u, v
+    noise = 2 * np.random.rand(rows, cols).astype(np.float32) - 1            # generate_matrix.py:122-125
+    s = 10 * np.sqrt(np.einsum('ij,ij->i', noise, noise))
+    a += np.reshape(sigma[-1] / s, (rows, 1)) * noise
+    del noise
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    try:
+        tmp = path + '.%d.tmp' % os.getpid()
+        with open(tmp, 'wb') as fh:
+            np.save(fh, a)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return a
+
+
+def generate_shard(rows, cols, rank, device, seed=1, world=1, shard=0):
+    """N > 1 (weak scaling: `rows` samples per GPU): the reference's generator cannot produce one shard of a
+    (world*rows) x cols matrix without forming all of it, so each rank draws its rows of a matrix of the same
+    recipe (examples/pca/generate_matrix.py:55-77, 122-125) with torch: A = U diag(k^-0.75) V^T + noise,
+    U[:, 0] = const, V common to all shards, U per shard scaled to stay (nearly) orthonormal globally."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -77,6 +127,23 @@ def generate_c2(rows, cols, rank, device, seed=1, world=1, shard=0):
     a += scale[:, None] * noise
     del noise
     return a.contiguous()
+
+
+def workload_config(args, world):
+    gen = ('reference generator examples/pca/generate_matrix.py generate(%d, %d, %d, alpha=0.75, pca=True) + --ptb noise, '
+           'numpy.random.seed(1)' % (args.rows, args.cols, RANK_GEN)) if world == 1 else \
+        'same recipe drawn per shard with torch (the reference generator cannot produce one shard of the global matrix)'
+    return {'workload': 'C2: PCA of synthetic %dx%d fp32 low-rank+noise (LFW 175x225 shape), %d components, '
+                        'block 128, svtol 1e-3%s' % (args.rows * world, args.cols, args.npc,
+                                                     '' if world == 1 else ' (%d rows per GPU)' % args.rows),
+            'generator': gen,
+            'l2_policy': 'inputs_exceed_l2 (data matrix %.2f GB streamed every operator application)'
+                         % (args.rows * args.cols * 4 / 1e9),
+            'parallelism': 'single GPU' if world == 1 else
+            'sample-partitioned data matrix over %d GPUs: row-sharded block vectors, NCCL all-reduce of Gram '
+            'matrices and of the k x n_features partial products' % world,
+            'solver': 'reference lra/partial_svd + Solver.solve unmodified; main loop and partial-SVD post-processing '
+                      'device-resident (raleigh_b200/jcg.py, psvd.py: no host LAPACK)'}
 
 
 def pca_error_gpu(a_dev, mean, trans, comps):
@@ -105,7 +172,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -139,123 +206,269 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference CPU path
-def load_reference_cpu():
-    """The reference package with its own CPU algebra (dense_cpu -> dense_numpy,
-    MKL being absent); only the SciPy `turbo` shim is applied."""
-    from raleigh_b200.compat import find_reference, shim_scipy, unshim_host_hotspots
-    path = find_reference()
-    if path is None:
-        return None
-    if path not in sys.path:
-        sys.path.insert(0, path)
-    shim_scipy()
-    unshim_host_hotspots()      # the GPU arm's vectorised `_norm` must not speed up the reference arm
-    return path
+def host_threads():
+    """All the host threads the process may use (torchrun pins OMP_NUM_THREADS=1 in its children)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
 
 
-def cpu_pca_seconds(a_host, npc, budget_s=60.0):
-    """Time the reference's CPU pca on the box's host cores.  Runs the FULL
-    workload when a calibration GEMM says it fits the budget, otherwise a
-    row/component-proportional sample, extrapolated (and labelled so)."""
+def cpu_pca_seconds(a_host, r, k, total_rows, npc):
+    """One solve with the reference's CPU pca on rows [0, r) with k components; returns (seconds extrapolated
+    to the full workload of total_rows x npc, description, components, singular values, iterations)."""
     import numpy as np
-    from raleigh.interfaces.pca import pca
-    from raleigh.core.solver import Options
-    rows, cols = a_host.shape
-    x = np.random.rand(128, cols).astype(np.float32)
-    t0 = time.perf_counter()
-    y = x @ a_host.T
-    _ = y @ a_host
-    t_pair = time.perf_counter() - t0
-    est = 22 * t_pair * (npc / 1000.0) + 3.0
-    frac = 1.0
-    if est > budget_s:
-        frac = max(0.1, (budget_s / est) ** 0.5)
-    r, k = int(rows * frac), max(8, int(npc * frac))
-    sample = a_host if frac == 1.0 else np.ascontiguousarray(a_host[:r])
     from raleigh.interfaces.lra import LowerRankApproximation
     from raleigh.algebra.dense_matrix import AMatrix
+    from raleigh.core.solver import Options
+    rows, cols = a_host.shape
+    sample = a_host if r == rows else np.ascontiguousarray(a_host[:r])
+    np.random.seed(1)
     t0 = time.perf_counter()
-    # exactly what pca(sample, npc=k, arch='cpu') does (pca.py:142-153), spelled out so that
-    # the solver's iteration count can be reported next to the GPU run's
+    # exactly what pca(sample, npc=k, arch='cpu') does (pca.py:142-153), spelled out so that the solver's
+    # iteration count can be reported next to the GPU run's
     lra = LowerRankApproximation()
     lra.ortho = 1e-3 if sample.shape[0] < sample.shape[1] else 0
     lra.compute(AMatrix(sample, arch='cpu'), opt=Options(), rank=k, tol=0, norm='f', max_rank=-1, svtol=1e-3,
                 shift=True, verb=0)
-    trans, comps, mean = lra.left(), lra.right(), lra.mean()
+    trans, comps = lra.left(), lra.right()
     t = time.perf_counter() - t0
-    cpu_pca_seconds.last_iterations = int(lra.iterations)
-    if frac == 1.0:
-        desc = 'full C2 workload: pca(%dx%d fp32, npc=%d), reference dense_numpy on NumPy/OpenBLAS (not MKL)' % (
-            rows, cols, npc)
-        return t, desc, comps.shape[0]
-    scale = (rows * npc) / float(r * k)
-    desc = ('rows 0..%d of the C2 matrix, npc=%d (%.1f s measured), scaled x%.2f by rows*components to the '
-            'full workload; reference dense_numpy on NumPy/OpenBLAS (not MKL)' % (r, k, t, scale))
-    return t * scale, desc, comps.shape[0]
+    sv = np.sqrt(np.einsum('ij,ij->j', trans.astype(np.float64), trans.astype(np.float64)))
+    lib = 'reference dense_numpy on NumPy/OpenBLAS (not MKL), %d threads' % host_threads()
+    if r == total_rows and k == npc:
+        desc = 'full workload: pca(%dx%d fp32, npc=%d), %s' % (rows, cols, npc, lib)
+        return t, desc, comps.shape[0], sv, int(lra.iterations)
+    scale = (total_rows * npc) / float(r * k)
+    desc = ('rows 0..%d of the %dx%d matrix, npc=%d (%.2f s measured), scaled x%.2f by rows*components to the full '
+            'workload; %s' % (r, total_rows, cols, k, t, scale, lib))
+    return t * scale, desc, comps.shape[0], sv, int(lra.iterations)
 
 
-# --------------------------------------------------------------------------- main arms
 def run_reference(args, rank, world):
+    """The reference arm: the reference's own CPU implementation of the path on the host cores.  Imports
+    NumPy / SciPy / the reference only -- no raleigh_b200, no CUDA."""
     if rank != 0:
         return
+    threads = host_threads()
+    for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[var] = str(threads)            # before NumPy loads its BLAS
     import numpy as np
-    ref = load_reference_cpu()
-    if ref is None:
-        print(json.dumps({'impl': 'reference', 'unavailable': 'reference package not on this box'}))
+    from tools import refenv
+    if refenv.load_reference() is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'reference package (baseline/_ref) not on this box'}))
         return
-    import torch
-    dev = 'cuda' if torch.cuda.is_available() else 'cpu'
-    a_host = generate_c2(args.rows, args.cols, RANK_GEN, dev).cpu().numpy()
-    np.random.seed(1)
-    budget = 240.0
-    times, desc = [], ''
-    warm = min(args.warmup, 1)
-    t_first, desc, ncomp = cpu_pca_seconds(a_host, args.npc)
-    if warm == 0:
-        times.append(t_first)
-    per = max(t_first, 1e-3)
-    while len(times) < args.steps and (len(times) + 1) * per < budget:
-        t, desc, ncomp = cpu_pca_seconds(a_host, args.npc)
-        times.append(t)
-    if not times:
-        times.append(t_first)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
+    t_gen = time.perf_counter()
+    if world == 1:
+        a_host = c2_host_matrix(args.rows, args.cols)
+    else:
+        import torch
+        torch.set_num_threads(threads)
+        a_host = generate_shard(args.rows, args.cols, RANK_GEN, 'cpu', seed=1, world=world, shard=0).numpy()
+    t_gen = time.perf_counter() - t_gen
+    total_rows = args.rows * world
+    # size of one step: the full workload when K + W of them fit the budget, else a row/component-proportional
+    # sample (cost ~ rows * components), extrapolated and labelled so
+    x = np.random.rand(128, args.cols).astype(np.float32)
+    t0 = time.perf_counter()
+    y = x @ a_host.T
+    _ = y @ a_host
+    t_pair = time.perf_counter() - t0
+    est_shard = 22 * t_pair * (args.npc / 1000.0) + 3.0            # one shard's rows, all components
+    nsteps = args.steps + min(args.warmup, 1)
+    per_step = max(REFERENCE_BUDGET_S - t_gen, 30.0) / max(nsteps, 1)
+    r, k = args.rows, args.npc                                      # at most one shard's rows are ever held
+    if not args.full and est_shard > per_step:
+        k = max(64, int(args.npc * per_step / est_shard))
+        if est_shard * k / args.npc > per_step:
+            r = max(512, int(args.rows * per_step / (est_shard * k / args.npc)))
+    times, desc, ncomp, sv, its = [], '', 0, None, None
+    for i in range(nsteps):
+        t, desc, ncomp, sv, its = cpu_pca_seconds(a_host, r, k, total_rows, args.npc)
+        if i >= min(args.warmup, 1):
+            times.append(t)
     val = sum(times) / len(times)
+    if args.sv_out:
+        np.save(args.sv_out, sv)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 's', 'n_gpus': args.gpus,
-        'steps': args.steps, 'steps_executed': len(times), 'warmup': args.warmup, 'ms_per_step': val * 1e3,
+        'steps': args.steps, 'steps_executed': len(times), 'warmup': args.warmup,
+        'warmup_executed': min(args.warmup, 1), 'ms_per_step': val * 1e3,
         'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': val / 27.0, 'dtype': 'f32',
-        'data': 'synthetic', 'config': dict(workload_config(args, 1), parallelism='host CPU, %d cores' % os.cpu_count(),
-                                                 solver='reference core solver + lra/partial_svd on the reference\'s own '
-                                                        'dense_numpy algebra (NumPy/OpenBLAS; MKL not installable)'),
-        'cpu_baseline': {'value': val, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference', 'sample': desc},
+        'data': 'synthetic',
+        'config': dict(workload_config(args, world), parallelism='host CPU, %d threads' % threads,
+                       solver='reference core solver + lra/partial_svd on the reference\'s own dense_numpy algebra '
+                              '(NumPy/OpenBLAS; MKL not installable)'),
+        'cpu_baseline': {'value': val, 'unit': 's', 'cores': threads, 'kind': 'reference', 'sample': desc},
         'e2e': {'value': val, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'components': int(ncomp), 'solver_iterations': getattr(cpu_pca_seconds, 'last_iterations', None),
+        'components': int(ncomp), 'solver_iterations': its, 'sample_rows': r, 'sample_components': k,
+        'generate_s': round(t_gen, 2),
     }
     print(json.dumps(line))
 
 
-def workload_config(args, world):
-    return {'workload': 'C2: PCA of synthetic %dx%d fp32 low-rank+noise (LFW 175x225 shape), %d components, '
-                        'block 128, svtol 1e-3%s' % (args.rows * world, args.cols, args.npc,
-                                                     '' if world == 1 else ' (%d rows per GPU)' % args.rows),
-            'l2_policy': 'inputs_exceed_l2 (data matrix %.2f GB streamed every operator application)'
-                         % (args.rows * args.cols * 4 / 1e9),
-            'parallelism': 'single GPU' if world == 1 else
-            'sample-partitioned data matrix over %d GPUs: row-sharded block vectors, NCCL all-reduce of Gram '
-            'matrices and of the k x n_features partial products' % world,
-            'solver': 'reference core solver + lra/partial_svd, unmodified, on raleigh_b200 backend'}
+def cpu_baseline_child(args):
+    """cpu_baseline leg of the GPU arm: the reference arm in a child process (fresh thread settings, no
+    product in the address space), one step; returns (record, singular values or None)."""
+    svf = os.path.join(tempfile.gettempdir(), 'raleigh_b200_cpu_sv_%d.npy' % os.getpid())
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+           '--rows', str(args.rows), '--cols', str(args.cols), '--npc', str(args.npc), '--sv-out', svf, '--full']
+    env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    t0 = time.perf_counter()
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+    rec = None
+    for ln in out.stdout.splitlines():
+        if ln.startswith('{'):
+            rec = json.loads(ln)
+    if rec is None or 'value' not in rec:
+        return {'value': None, 'unit': 's', 'cores': host_threads(), 'kind': 'reference',
+                'sample': 'failed: %s' % (out.stderr[-300:],)}, None
+    sv = None
+    try:
+        import numpy as np
+        sv = np.load(svf)
+        os.remove(svf)
+    except Exception:
+        pass
+    base = dict(rec['cpu_baseline'])
+    base['solver_iterations'] = rec.get('solver_iterations')
+    base['components'] = rec.get('components')
+    base['wall_s_including_generation'] = round(time.perf_counter() - t0, 1)
+    return base, sv
 
 
+# --------------------------------------------------------------------------- bounded config 4
+def lap3d_rows(N, row0, nloc):
+    """Rows [row0, row0+nloc) of the 7-point Laplacian on an N^3 grid (h = 1/(N+1), x fastest; the operator of
+    examples/laplace.py:23-27) as CSR arrays built directly -- sorted columns, no COO pass, no global matrix."""
+    import numpy as np
+    import scipy.sparse as sp
+    h2 = float(N + 1) ** 2
+    r = np.arange(row0, row0 + nloc, dtype=np.int64)
+    x, y, z = r % N, (r // N) % N, r // (N * N)
+    offs = np.array([-N * N, -N, -1, 0, 1, N, N * N], dtype=np.int64)
+    valid = np.stack([z > 0, y > 0, x > 0, np.ones(nloc, dtype=bool), x < N - 1, y < N - 1, z < N - 1], axis=1)
+    del x, y, z
+    cols = (r[:, None] + offs[None, :])[valid].astype(np.int32 if N ** 3 < 2 ** 31 else np.int64)
+    vals = np.broadcast_to(np.array([-h2, -h2, -h2, 6.0 * h2, -h2, -h2, -h2]), (nloc, 7))[valid]
+    indptr = np.zeros(nloc + 1, dtype=np.int64)
+    np.cumsum(valid.sum(axis=1), out=indptr[1:])
+    A = sp.csr_matrix((vals, cols, indptr), shape=(nloc, N ** 3))
+    A.has_sorted_indices = True
+    return A
+
+
+class _StopAfter:
+    def __init__(self, iters):
+        self.iters = iters
+
+    def satisfied(self, solver):
+        return solver.iteration + 1 >= self.iters
+
+
+def c4_leg(args, rank, world, ctx):
+    """Bounded BASELINE config 4: 3D Laplacian grid^3 row-sharded over the ranks, a FIXED number of iterations of
+    the device-resident block-CG driver (a full solve needs > 1000 iterations at 256^3) at
+    block 32 and at the block the solver picks for 100 wanted pairs (120).  Per-iteration wall and device time,
+    SpMM / Gram / update GB/s per rank from the library's CUDA-event spans, halo and all-reduce traffic."""
+    import numpy as np
+    import torch
+    import raleigh_b200 as rb
+    from raleigh_b200 import dist as rdist, profile
+    import raleigh.core.solver as rs
+    import torch.distributed as tdist
+    N = args.c4_grid
+    n = N ** 3
+    t0 = time.perf_counter()
+    if world > 1:
+        row0, nloc = rdist.partition(n, world, rank)
+    else:
+        row0, nloc = 0, n
+    op = rb.SparseSymmetricMatrix(lap3d_rows(N, row0, nloc), local_rows=(row0, n))
+    torch.cuda.synchronize()
+    setup = time.perf_counter() - t0
+    out = {'grid': '%d^3' % N, 'rows': n, 'rows_per_gpu': nloc, 'nnz_per_gpu': op.nnz(), 'dtype': 'f64',
+           'operator_setup_s': round(setup, 2), 'iterations_run': args.c4_iters,
+           'note': 'bounded: fixed iteration count, no convergence claimed'}
+
+    def run(block, nev, iters):
+        np.random.seed(1)
+        opt = rs.Options()
+        opt.block_size = block
+        opt.max_iter = 10 ** 6
+        opt.verbosity = -1
+        opt.convergence_criteria = rs.DefaultConvergenceCriteria()
+        opt.convergence_criteria.set_error_tolerance('k eigenvector error', 1e-6)
+        opt.stopping_criteria = _StopAfter(iters)
+        v = rb.Vectors(n, data_type=np.float64)
+        solver = rs.Solver(rs.Problem(v, op))
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+        t = time.perf_counter()
+        solver.solve(v, opt, which=(nev, 0))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        return dt, solver
+
+    free, _ = torch.cuda.mem_get_info()
+    for block, nev in ((32, 20), (120, 100)):
+        need = 9.5 * nloc * block * 8 + (2 << 30)
+        key = 'block%d' % block
+        if need > free:
+            out[key] = {'skipped': 'needs %.0f GB per GPU, %.0f GB free' % (need / 1e9, free / 1e9)}
+            continue
+        try:
+            run(block, nev, 2)                                   # warm-up: allocator, NCCL channels, plans
+            profile.reset()
+            profile.enable(True)
+            if ctx is not None:
+                ctx.allreduce_calls = ctx.allreduce_bytes = 0
+            op.halo_bytes = 0
+            dt, solver = run(block, nev, args.c4_iters)
+            profile.enable(False)
+            prof = profile.report()
+            its = max(int(solver.iteration) + 1, 1)
+            if world > 1:
+                t = torch.tensor([dt], device='cuda')
+                tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+                dt = t.item()
+            rec = {'seconds_per_iteration': round(dt / its, 5), 'iterations': its,
+                   'device_ms_per_iteration': round(sum(v['ms'] for v in prof.values()) / its, 3),
+                   'kernels': {k: {'count': v['count'], 'ms': round(v['ms'], 2), 'GBps': round(v['GBps'], 1)}
+                               for k, v in prof.items() if k in ('spmm', 'gram', 'update', 'dots', 'rr_solve', 'piv_chol')}}
+            if ctx is not None:
+                rec['nccl'] = {'allreduce_calls_per_iteration': round(ctx.allreduce_calls / its, 1),
+                               'allreduce_KB_per_iteration': round(ctx.allreduce_bytes / its / 1e3, 1),
+                               'halo_MB_per_iteration': round(getattr(op, 'halo_bytes', 0) / its / 1e6, 2)}
+            out[key] = rec
+        except Exception as exc:                                 # the leg must never cost the headline line
+            out[key] = {'error': repr(exc)[:300]}
+        torch.cuda.empty_cache()
+    if ctx is not None:
+        g = torch.zeros(240 * 240, dtype=torch.float64, device='cuda')
+        for _ in range(3):
+            tdist.all_reduce(g)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            tdist.all_reduce(g)
+        b.record()
+        torch.cuda.synchronize()
+        out['allreduce_240x240_f64_ms'] = round(a.elapsed_time(b) / 20, 4)
+    return out
+
+
+# --------------------------------------------------------------------------- GPU arm
 def run_b200(args, rank, world, local_rank):
-    """GPU arm.  The host keeps only the solver's k x k algebra (<= 256 x 256), for
-    which multi-threaded BLAS/LAPACK is slower than one thread (SURVEY.md section 6:
-    8 threads were 3x slower than 1 on config 1; torchrun pins OMP_NUM_THREADS=1
-    anyway), so host BLAS is limited to one thread here; the CPU baseline below
-    gets all cores back."""
     import numpy as np
     import torch
     from threadpoolctl import threadpool_limits
-    host_limit = threadpool_limits(limits=1)
+    host_limit = threadpool_limits(limits=1)         # the host keeps only length-m bookkeeping
     torch.cuda.set_device(local_rank)
     import raleigh_b200 as rb
     from raleigh_b200 import profile, cuda
@@ -294,9 +507,13 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    a_dev = generate_c2(args.rows, args.cols, RANK_GEN, 'cuda', seed=1, world=world, shard=rank)
     a_pinned = torch.empty((args.rows, args.cols), dtype=torch.float32, pin_memory=True)
-    a_pinned.copy_(a_dev)
+    if world == 1:
+        a_pinned.copy_(torch.from_numpy(c2_host_matrix(args.rows, args.cols)))
+        a_dev = a_pinned.cuda()
+    else:
+        a_dev = generate_shard(args.rows, args.cols, RANK_GEN, 'cuda', seed=1, world=world, shard=rank)
+        a_pinned.copy_(a_dev)
     a_host = a_pinned.numpy()
     torch.cuda.synchronize()
 
@@ -343,19 +560,28 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop(t0, t1) if sampler else None
     iterations = int(lra.iterations)
     ncomp = int(lra.left_v().nvec())
-    del matrix
+    del matrix, lra
 
     # ---- end-to-end arm
     for _ in range(min(args.warmup, 3)):
         res = solve_e2e()
     ms_e2e, res, _, _ = timed(solve_e2e, args.steps)
     mean, trans, comps = res
+    sv_gpu = np.sqrt(np.einsum('ij,ij->j', trans.astype(np.float64), trans.astype(np.float64)))
     if world > 1:      # `trans` is gathered over ranks: check this rank's rows against its slab
         trans = trans[rank * args.rows:(rank + 1) * args.rows]
     em, ef = pca_error_gpu(a_dev, mean, trans, comps)
     h2d = a_host.nbytes
-    d2h = trans.nbytes + comps.nbytes + mean.nbytes
+    d2h = res[1].nbytes + comps.nbytes + mean.nbytes
+    del a_dev
+    torch.cuda.empty_cache()
 
+    c4 = None
+    if not args.no_c4:
+        try:
+            c4 = c4_leg(args, rank, world, ctx)
+        except Exception as exc:
+            c4 = {'error': repr(exc)[:300]}
     if rank != 0:
         return
     peaks = {}
@@ -390,44 +616,47 @@ def run_b200(args, rank, world, local_rank):
         line['hbm_kernels'] = hbm_kernel_rates(peaks.get('hbm_gbs') or 6650.0)
     except Exception as exc:
         line['hbm_kernels'] = {'error': repr(exc)}
+    if c4 is not None:
+        line['c4'] = c4
     line['impl'] = 'raleigh_b200'
     if ctx is not None:
         line['collectives'] = {'allreduce_calls': ctx.allreduce_calls, 'allreduce_MB': round(ctx.allreduce_bytes / 1e6, 1)}
     host_limit.restore_original_limits()
     if world == 1 and not args.no_cpu_baseline:
         try:
-            load_reference_cpu()
-            np.random.seed(1)
-            t, desc, _ = cpu_pca_seconds(a_host, args.npc, budget_s=45.0)
-            line['cpu_baseline'] = {'value': t, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference',
-                                    'sample': desc,
-                                    'solver_iterations': getattr(cpu_pca_seconds, 'last_iterations', None)}
+            base, sv_cpu = cpu_baseline_child(args)
+            line['cpu_baseline'] = base
+            if sv_cpu is not None and len(sv_cpu) == len(sv_gpu):
+                rel = np.abs(sv_gpu - sv_cpu) / sv_cpu
+                line['max_rel_sv_diff'] = {'leading_100': float(rel[:100].max()), 'all': float(rel.max()),
+                                           'note': 'singular values (column norms of the scores) of the GPU arm vs the '
+                                                   'cpu_baseline run on the same matrix; both solve to svtol = 1e-3, so '
+                                                   'the trailing values differ at that level between any two runs'}
         except Exception as exc:  # the baseline must never cost us the measured line
-            line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'reference',
+            line['cpu_baseline'] = {'value': None, 'unit': 's', 'cores': host_threads(), 'kind': 'reference',
                                     'sample': 'failed: %r' % (exc,)}
     print(json.dumps(line))
 
 
 def hbm_kernel_rates(peak_gbs):
     """Block-SpMM and Gram bandwidth (the second half of BASELINE.json's metric) on the
-    per-GPU block of config 4 at block size 32: n = 2,097,152 rows (256^3 / 8), fp64,
-    7-point Laplacian slab of 128^3.  CUDA events around the C-ABI calls, L2 flushed
+    per-GPU block of config 4: n = 2,097,152 rows (256^3 / 8), fp64, 7-point Laplacian slab of 128^3, block 32
+    (and the Gram product at block 120).  CUDA events around the C-ABI calls, L2 flushed
     between repetitions.  A few milliseconds in total; outside every timed region."""
     import numpy as np
     import torch
     import raleigh_b200 as rb
     from raleigh_b200._lib import lib, check
     from raleigh_b200 import device as dev
-    import scipy.sparse as sp
     from raleigh_b200 import dist as rdist
     saved, rdist._current = rdist._current, None     # single-GPU micro-measurement: no sharding, no collectives
     try:
-        return _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp)
+        return _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev)
     finally:
         rdist._current = saved
 
 
-def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
+def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
     def timed(fn, reps=5, write_flush=True):
@@ -444,53 +673,57 @@ def _hbm_kernel_rates(peak_gbs, np, torch, rb, lib, check, dev, sp):
         return best[len(best) // 2]
 
     out = {}
-    n, m = 2097152, 32
-    X, Y = rb.Vectors(n, m), rb.Vectors(n, m)
-    X.fill_random_device(1)
-    Y.fill_random_device(2)
-    wsb = lib.rl_gram_ws_bytes(1, m, m, n)
-    ws, g = dev.Buffer(wsb), dev.Buffer(m * m * 8)
-    ms = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
-                                         dev.stream())))
-    by = 2.0 * n * m * 8
-    out['gram'] = {'shape': 'n=%d, m=k=%d, fp64' % (n, m), 'ms': ms, 'GBps': by / ms / 1e6,
-                   'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs, 'TFLOPs': 2.0 * n * m * m / ms / 1e9}
-    # second reading without the write flush: the inputs (1.07 GB) exceed L2 (126 MB) on their own
-    # (measured r1e: 0.247 ms vs 0.236 ms after the flush -- the flush does not penalise the kernel)
-    ms2 = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
-                                          dev.stream())), write_flush=False)
-    out['gram'].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
-    N = 128
-
-    def lap1(k):
-        return sp.diags([-np.ones(k - 1), 2 * np.ones(k), -np.ones(k - 1)], [-1, 0, 1], format='csr')
-    I = sp.identity(N, format='csr')
-    L = (sp.kron(I, sp.kron(I, lap1(N))) + sp.kron(I, sp.kron(lap1(N), I)) + sp.kron(lap1(N), sp.kron(I, I))).tocsr()
-    A = rb.SparseSymmetricMatrix(L)
-    ms = timed(lambda: A.apply(X, Y))
-    nnz = A.nnz()
-    by = nnz * 12.0 + (n + 1) * 8.0 + 2.0 * n * m * 8
-    out['spmm'] = {'shape': '7-point Laplacian 128^3 (n=%d, nnz=%d), m=%d, fp64, %s' % (n, nnz, m, A.layout()),
-                   'ms': ms, 'GBps': by / ms / 1e6, 'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs}
-    ms2 = timed(lambda: A.apply(X, Y), write_flush=False)
-    out['spmm'].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
+    n = 2097152
+    for m in (32, 120):
+        X, Y = rb.Vectors(n, m), rb.Vectors(n, m)
+        X.fill_random_device(1)
+        Y.fill_random_device(2)
+        wsb = lib.rl_gram_ws_bytes(1, m, m, n)
+        ws, g = dev.Buffer(wsb), dev.Buffer(m * m * 8)
+        ms = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
+                                             dev.stream())))
+        by = 2.0 * n * m * 8
+        key = 'gram' if m == 32 else 'gram_block120'
+        out[key] = {'shape': 'n=%d, m=k=%d, fp64' % (n, m), 'ms': ms, 'GBps': by / ms / 1e6,
+                    'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs, 'TFLOPs': 2.0 * n * m * m / ms / 1e9}
+        if m == 32:
+            # second reading without the write flush: the inputs (1.07 GB) exceed L2 (126 MB) on their own
+            ms2 = timed(lambda: check(lib.rl_gram(1, X._wptr(), X._ld, m, Y._wptr(), Y._ld, m, n, g.ptr, ws.ptr, wsb,
+                                                  dev.stream())), write_flush=False)
+            out[key].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
+            A = rb.SparseSymmetricMatrix(lap3d_rows(128, 0, n), local_rows=(0, n))
+            ms = timed(lambda: A.apply(X, Y))
+            nnz = A.nnz()
+            by = nnz * 12.0 + (n + 1) * 8.0 + 2.0 * n * m * 8
+            out['spmm'] = {'shape': '7-point Laplacian 128^3 (n=%d, nnz=%d), m=%d, fp64, %s' % (n, nnz, m, A.layout()),
+                           'ms': ms, 'GBps': by / ms / 1e6, 'frac_of_measured_hbm_peak': by / ms / 1e6 / peak_gbs}
+            ms2 = timed(lambda: A.apply(X, Y), write_flush=False)
+            out['spmm'].update({'ms_inputs_exceed_l2_no_flush': ms2, 'frac_no_flush': by / ms2 / 1e6 / peak_gbs})
+            del A
+        del X, Y
     return out
 
 
 def roofline_from(prof, peaks, steps):
-    """Dominant kernel of the step by device time; tensor-bound dense operator
-    application for this workload."""
+    """Roofline of the dominant HOT-PATH kernel of the step by device time: the dense operator application
+    (tensor-bound) for this workload.  The Rayleigh-Ritz spans (rr_solve, piv_chol, syevj) are chains of
+    latency-bound small kernels with no bandwidth / flop roofline of their own; their share of the device time
+    is reported next to it."""
     if not prof:
         return None
-    name = max(prof, key=lambda k: prof[k]['ms'])
+    total = sum(v['ms'] for v in prof.values())
+    sized = {k: v for k, v in prof.items() if k not in ('rr_solve', 'piv_chol', 'syevj', 'small_dense')}
+    name = max(sized, key=lambda k: sized[k]['ms'])
     rec = prof[name]
+    small = {k: round(prof[k]['ms'] / total, 3) for k in ('rr_solve', 'piv_chol', 'syevj', 'small_dense') if k in prof}
     if name.startswith('dense_apply'):
         peak = peaks.get('bf16_tflops_sustained') or 1400.0
         src = 'measured sustained bf16 (MEASURED_PEAKS.json)' if 'bf16_tflops_sustained' in peaks else 'fallback'
         return {'kernel': name, 'bound': 'tensor', 'achieved': rec['TFLOPs'], 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': rec['TFLOPs'] / peak, 'traffic': None, 'launches': rec['count'],
-                'avg_launch_ms': rec['ms'] / rec['count'], 'share_of_device_time': rec['ms'] / sum(
-                    v['ms'] for v in prof.values()),
+                'avg_launch_ms': rec['ms'] / rec['count'], 'share_of_device_time': rec['ms'] / total,
+                'small_dense_algebra_share_of_device_time': small,
+                'algorithmic_GBps': rec['GBps'],
                 'peak_source': src,
                 'note': 'fp32 result via tensor cores needs a 3xTF32 split: the attainable ceiling is '
                         'tf32 peak / 3 = bf16 peak / 6; HBM floor of this GEMM: %.2f ms per launch'
@@ -498,7 +731,8 @@ def roofline_from(prof, peaks, steps):
     peak = peaks.get('hbm_gbs') or 6650.0
     return {'kernel': name, 'bound': 'hbm', 'achieved': rec['GBps'], 'peak': peak, 'unit': 'GB/s',
             'frac': rec['GBps'] / peak, 'traffic': None, 'launches': rec['count'],
-            'avg_launch_ms': rec['ms'] / rec['count'],
+            'avg_launch_ms': rec['ms'] / rec['count'], 'share_of_device_time': rec['ms'] / total,
+            'small_dense_algebra_share_of_device_time': small,
             'peak_source': 'measured copy bandwidth (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback'}
 
 

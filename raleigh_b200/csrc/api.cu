@@ -10,6 +10,7 @@ namespace rl {
 
 int64_t g_launches = 0;
 int g_profile_on = 0;
+int g_span_depth = 0;
 int g_knob[KNOB_COUNT] = {0};
 
 namespace {
@@ -18,7 +19,7 @@ std::vector<ProfRec*> g_prof_open;           // spans recorded since the last co
 struct ProfSum { int64_t count = 0; double ms = 0, bytes = 0, flops = 0; } g_prof_sum[PK_COUNT];
 const char* kProfNames[PK_COUNT] = {"gram", "update", "axpy", "axpy_diag", "scale", "dots", "dots_t", "copy",
                                     "gather", "diag_mul", "spmm", "dense_apply", "dense_apply_tc", "syevj",
-                                    "fill_uniform"};
+                                    "fill_uniform", "piv_chol", "rr_solve", "small_dense"};
 void prof_collect() {
     if (g_prof_open.empty()) return;
     cudaDeviceSynchronize();

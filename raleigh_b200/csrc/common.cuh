@@ -94,18 +94,27 @@ __device__ __forceinline__ T warp_sum(T v) {
 // live from these); it costs one branch when profiling is off.
 enum ProfKind {
     PK_GRAM = 0, PK_UPDATE, PK_AXPY, PK_AXPY_DIAG, PK_SCALE, PK_DOTS, PK_DOTS_T, PK_COPY, PK_GATHER,
-    PK_DIAG_MUL, PK_SPMM, PK_DENSE_APPLY, PK_DENSE_APPLY_TC, PK_SYEVJ, PK_FILL, PK_COUNT
+    PK_DIAG_MUL, PK_SPMM, PK_DENSE_APPLY, PK_DENSE_APPLY_TC, PK_SYEVJ, PK_FILL, PK_PIV_CHOL, PK_RR_SOLVE, PK_SMALL,
+    PK_COUNT
 };
 extern int g_profile_on;
 void prof_begin(int kind, cudaStream_t st, double bytes, double flops, void** token);
 void prof_end(void* token, cudaStream_t st);
+extern int g_span_depth;            // only the outermost span of a call records (rl_rr_solve contains eigensolver calls)
 struct Span {
     void* token = nullptr;
     cudaStream_t st;
+    bool counted = false;
     Span(int kind, cudaStream_t s, double bytes, double flops) : st(s) {
-        if (g_profile_on) prof_begin(kind, s, bytes, flops, &token);
+        if (g_profile_on) {
+            counted = true;
+            if (g_span_depth++ == 0) prof_begin(kind, s, bytes, flops, &token);
+        }
     }
-    ~Span() { if (token) prof_end(token, st); }
+    ~Span() {
+        if (counted) --g_span_depth;
+        if (token) prof_end(token, st);
+    }
 };
 
 // Library-owned scratch: a pinned host ring + a device ring used by the *_h

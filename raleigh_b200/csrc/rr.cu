@@ -978,6 +978,7 @@ int rl_small_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, doubl
     if (M == 0 || N == 0) return 0;
     dim3 grid((unsigned)((N + SG_T - 1) / SG_T), (unsigned)((M + SG_T - 1) / SG_T));
     cudaStream_t st = as_stream(stream);
+    Span span(PK_SMALL, st, (1.0 * M * K + 1.0 * K * N + 2.0 * M * N) * 8, 2.0 * M * N * K);
     if (transa && transb) small_gemm_kernel<true, true><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (transa) small_gemm_kernel<true, false><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (transb) small_gemm_kernel<false, true><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -989,6 +990,7 @@ int rl_small_trsm(int mode, const double* U, int64_t ldu, int64_t n, double* B, 
                   void* stream) {
     if (n < 0 || r < 0 || (mode != 0 && mode != 1)) return RL_E_ARG;
     if (n == 0 || r == 0) return 0;
+    Span span(PK_SMALL, as_stream(stream), (0.5 * n * n + 2.0 * n * r) * 8, 1.0 * n * n * r);
     small_trsm_kernel<<<(unsigned)((r + 31) / 32), 256, 0, as_stream(stream)>>>(U, ldu, (int)n, B, ldb, (int)r, mode);
     return check_launch();
 }
@@ -1137,6 +1139,7 @@ int rl_rr_piv_chol(double* a, double* a0, int64_t ld, int64_t n, int64_t k, doub
     if (n < 0 || k < 0 || k > n || n > 4096) return RL_E_ARG;
     cudaStream_t st = as_stream(stream);
     if (n == 0) return (int)cudaMemsetAsync(info, 0, 4 * sizeof(int), st);
+    Span span(PK_PIV_CHOL, st, 2.0 * n * n * 8, 1.0 * n * n * n / 3.0);
     const int64_t ny = n - k;
     if (k <= CH_SMEM_MAX && ny <= CH_SMEM_MAX && g_knob[KNOB_CHOL_GLOBAL] == 0) {
         static bool configured = false;
@@ -1228,6 +1231,7 @@ int rl_small_potrf(double* a, int64_t ld, int64_t n, int* info_d, void* stream) 
     cudaStream_t st = as_stream(stream);
     RL_CUDA(cudaMemsetAsync(info_d, 0, sizeof(int), st));
     if (n == 0) return 0;
+    Span span(PK_SMALL, st, 2.0 * n * n * 8, 1.0 * n * n * n / 3.0);
     const int64_t NB = 128;
     static bool configured = false;
     if (!configured) {

@@ -110,6 +110,7 @@ int rl_rr_solve(const double* ga, const double* u, int64_t ld, int64_t nx, int64
     if (n == 0) return 0;
     if (ws_bytes < rl_rr_solve_ws_bytes(nmax)) return RL_E_WORKSPACE;
     cudaStream_t st = as_stream(stream);
+    Span span(PK_RR_SOLVE, st, 5.0 * n * n * 8, 8.0 * n * n * n);
     const size_t mat = align256((size_t)nmax * nmax * sizeof(double)), vecb = align256((size_t)nmax * sizeof(double));
     char* p = (char*)ws;
     double* W1 = (double*)p; p += mat;

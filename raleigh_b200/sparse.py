@@ -35,11 +35,16 @@ class SparseSymmetricMatrix:
         ctx = dist.current()
         self.__plan = None
         if local_rows is not None:
-            if ctx is None:
-                raise ValueError('local_rows needs an active ShardContext')
             row0, n_global = int(local_rows[0]), int(local_rows[1])
             slab = matrix.tocsr()
-            slab.sort_indices()
+            if not slab.has_sorted_indices:
+                slab.sort_indices()
+            if ctx is None or ctx.world == 1 or not ctx.shard_matrices:
+                # single process: `matrix` must be ALL rows of the full symmetric operator (no triu / mirror pass:
+                # config 4's 117 M entries are generated directly in this form)
+                if row0 != 0 or slab.shape[0] != n_global:
+                    raise ValueError('local_rows without an active ShardContext needs the whole operator')
+                full = slab
             csr = None
             self.__n = n_global
         else:

@@ -292,9 +292,11 @@ def test_device_pca_wide_matrix_uses_finalize(gpu_backend, ref):
     lead = slice(0, 30)
     # two fp32 computations of the same quantities: north_star's 1e-5 plus their own rounding
     assert np.max(np.abs(sv1[lead] - sv0[lead]) / sv0[lead]) < 2e-5
-    # and both sit on the exact singular values of the centred matrix to the solver's own tolerance (svtol)
+    # and both sit on the exact singular values of the centred matrix to the solver's own tolerance
+    # (svtol = 1e-3 on the vectors: measured 6e-6 on the first value, 6e-4 on the tenth, for either path)
     exact = np.linalg.svd(A.astype(np.float64) - A.astype(np.float64).mean(axis=0), compute_uv=False)
-    assert np.max(np.abs(sv1[:10] - exact[:10]) / exact[:10]) < 1e-4
+    assert np.max(np.abs(sv1[:10] - exact[:10]) / exact[:10]) < 2e-3
+    assert np.max(np.abs(sv0[:10] - exact[:10]) / exact[:10]) < 2e-3
     e0, e1 = pca_error(A, m0, t0, c0), pca_error(A, m1, t1, c1)
     assert abs(e0[0] - e1[0]) < 2e-3 and abs(e0[1] - e1[1]) < 2e-3
     assert np.max(np.abs(c1 @ c1.T - np.eye(c1.shape[0]))) < 1e-4
