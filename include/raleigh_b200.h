@@ -330,10 +330,10 @@ size_t rl_syevj_cluster_ws_bytes(int64_t n);
 int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, int factor_mode, double tol, double* w,
                      double* q, int64_t ldq, void* ws, size_t ws_bytes, int* info_d, void* stream);
 size_t rl_small_eigh_ws_bytes(int64_t n);
-int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq,
-                  void* ws, size_t ws_bytes, int* info_d, void* stream);
-int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double* w, double* q, int64_t ldq,
-                         void* ws, size_t ws_bytes, int* info_d, void* stream);
+int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double tol, double* w, double* q,
+                  int64_t ldq, void* ws, size_t ws_bytes, int* info_d, void* stream);
+int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double tol, double* w, double* q,
+                         int64_t ldq, void* ws, size_t ws_bytes, int* info_d, void* stream);
 /* unpivoted Cholesky factorisation G = U^T U of an n x n fp64 matrix in place (upper factor, zeros
  * below; numpy.linalg.cholesky at partial_svd.py:192), blocked: diagonal blocks in shared memory,
  * panels by rl_small_trsm, trailing update by rl_small_gemm.  info_d[0] = 0 or 1 + index of the

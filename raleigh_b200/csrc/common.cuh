@@ -17,13 +17,15 @@ extern int64_t g_launches;          // kernels launched by this library (api.cu)
 //  SPMM_CARVEOUT: shared-memory carve-out in percent; SPMM_WPS: 16 = 127-register budget + 4-entry batches,
 //            24 = 80 registers + 2-entry batches; SPMM_PREFETCH: -1 off, bit 0 largest-column lines,
 //            bit 1 CSR entries of the run one resident window ahead, bit 2 X lines shifted by that window;
-//  SPMM_WINDOW: 1 = experimental band-window kernel (spmm_win.cu), SPMM_WIN_CHUNKS: its CTAs per SM slot;
+//  (knobs 6, 7: the r1 band-window SpMM experiment, measured 0.60 vs 0.33 ms on the 128^3 stencil in r2a and removed;
+//   profiles/r2a_sweep_spmm_window.jsonl)
 //  GEMM_INSPLIT: 1 = experimental in-kernel lo split of the tcgen05 dense apply (gemm_tc.cu)
+//  GEMM_SKINNY: -1 = dense applies with k <= 8 vectors stay on the tiled FMA kernel (gemm_simt.cu);
 //  BLOCK_TC: -1 = fp32 Gram / block update of the device-resident driver never on the tensor cores;
 //  CHOL_GLOBAL: 1 = pivoted Cholesky always in global memory (the shared-memory split is the default);
 //  EIG_LEGACY: 1 = always use the cooperative-grid two-sided Jacobi kernel (small.cu) instead of the cluster kernel
 enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_SPMM_WINDOW = 6, KNOB_SPMM_WIN_CHUNKS = 7, KNOB_GEMM_INSPLIT = 8,
-            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_COUNT = 16 };
+            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_GEMM_SKINNY = 12, KNOB_COUNT = 16 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 

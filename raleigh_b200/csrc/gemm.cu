@@ -13,6 +13,9 @@ int split_tf32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int
 template <typename T>
 int gemm_simt(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
               int64_t k, int transp, double alpha, double beta, cudaStream_t st);
+template <typename T>
+int gemm_skinny(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
+                int64_t k, int transp, double alpha, double beta, cudaStream_t st);
 }
 
 using namespace rl;
@@ -26,8 +29,14 @@ int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N, 
     cudaStream_t st = as_stream(stream);
     const double w = dtype == RL_F32 ? 4.0 : 8.0;
     Span span(PK_DENSE_APPLY, st, (1.0 * M * N + 1.0 * k * (M + N)) * w, 2.0 * M * N * k);
-    if (dtype == RL_F32) return gemm_simt<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
-    if (dtype == RL_F64) return gemm_simt<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+    // a handful of vectors: HBM-bound matrix-vector sweep (gemm_skinny.cu); knob GEMM_SKINNY = -1 keeps the tiled kernel
+    const bool skinny = k <= 8 && M * N >= 4096 && g_knob[KNOB_GEMM_SKINNY] >= 0 && y != x;
+    if (dtype == RL_F32)
+        return skinny ? gemm_skinny<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st)
+                      : gemm_simt<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+    if (dtype == RL_F64)
+        return skinny ? gemm_skinny<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st)
+                      : gemm_simt<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
     return RL_E_DTYPE;
 }
 

@@ -62,13 +62,13 @@ jacobi_shift_kernel(const double* __restrict__ G, int64_t ld, int n, double* __r
 // division and one rsqrt for the cosine: the dependent chain of double-precision special functions is
 // what a round costs, so the textbook form (two divisions, two square roots, one reciprocal) is avoided.
 __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol2, double& c,
-                                                double& s) {
-    c = 1.0; s = 0.0;
+                                                double& s, double& t) {
+    c = 1.0; s = 0.0; t = 0.0;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;      // also false for zero (padding) columns
     const double delta = beta - alpha;
     const double h = fma(delta, delta, 4.0 * gamma * gamma);
     const double den = fabs(delta) + h * rsqrt(h);
-    const double t = (delta >= 0.0 ? 2.0 : -2.0) * gamma / den;
+    t = (delta >= 0.0 ? 2.0 : -2.0) * gamma / den;
     c = rsqrt(fma(t, t, 1.0));
     s = c * t;
     return true;
@@ -177,8 +177,8 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
                     beta += __shfl_xor_sync(0xffffffffu, beta, o);
                     gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
                 }
-                double c, s;
-                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
+                double c, s, t;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, t)) {
                     rot = 1;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
@@ -220,10 +220,9 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
                     beta += __shfl_xor_sync(0xffffffffu, beta, o2);
                     gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
                 }
-                double c, s;
-                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
+                double c, s, t;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, t)) {
                     rot = 1;
-                    double na = 0.0;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         double2 x, y;
@@ -231,12 +230,10 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
                         y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
                         p[j] = x;
                         cb[lane + 32 * j] = y;
-                        na = fma(x.x, x.x, na); na = fma(x.y, x.y, na);
                     }
-                    // the norm of the register-resident column is recomputed, not updated: no drift
-#pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o2);
-                    alpha = na;
+                    // |p'|^2 = |p|^2 - t <p, q> exactly; recomputed from the column at the start of every outer
+                    // round (at most W updates apart), so the shortcut cannot drift
+                    alpha = fma(-t, gamma, alpha);
                 }
                 __syncthreads();
             }
@@ -384,8 +381,8 @@ jacobi_grid_kernel(double* __restrict__ bt, int64_t ldb, int n, double tol, int*
                     beta += __shfl_xor_sync(0xffffffffu, beta, o);
                     gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
                 }
-                double c, s;
-                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s)) {
+                double c, s, t;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, t)) {
                     rot = 1;
 #pragma unroll
                     for (int j = 0; j < NQ; ++j) {

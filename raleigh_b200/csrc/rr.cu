@@ -318,16 +318,20 @@ __device__ void tri_solve_vec(const double* __restrict__ U, int64_t ld, int p, d
         if (warp == 0) {
             const int g = j0 + lane;
             double xv = g < p ? v[g] : 0.0;
+            // one division per lane instead of one per elimination step on the critical path
+            const double rinv = 1.0 / tile[lane][lane];
             if (forward) {
+#pragma unroll 8
                 for (int t = 0; t < 32; ++t) {
-                    const double yt = __shfl_sync(0xffffffffu, xv, t) / tile[t][t];
+                    const double yt = __shfl_sync(0xffffffffu, xv, t) * __shfl_sync(0xffffffffu, rinv, t);
                     if (lane == t) xv = yt;
                     else if (lane > t) xv = fma(-tile[t][lane], yt, xv);     // U[t][s], s > t
                 }
             } else {
                 xv -= part[lane];
+#pragma unroll 8
                 for (int t = 31; t >= 0; --t) {
-                    const double xt = __shfl_sync(0xffffffffu, xv, t) / tile[t][t];
+                    const double xt = __shfl_sync(0xffffffffu, xv, t) * __shfl_sync(0xffffffffu, rinv, t);
                     if (lane == t) xv = xt;
                     else if (lane < t) xv = fma(-tile[lane][t], xt, xv);     // U[s][t], s < t
                 }
@@ -358,7 +362,8 @@ __device__ double cond_inverse(const double* __restrict__ U, const double* __res
     for (int c = tid; c < p; c += blockDim.x) {
         const double* row = A0 + (int64_t)ind[c] * ld;          // symmetric: column c == row c
         double s = 0.0;
-        for (int r = 0; r < p; ++r) s += fabs(row[ind[r]]);
+#pragma unroll 8
+        for (int r = 0; r < p; ++r) s += fabs(__ldg(row + ind[r]));
         cmax = fmax(cmax, s);
     }
     for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
@@ -530,13 +535,14 @@ chol_lead_smem_kernel(double* __restrict__ A, double* __restrict__ A0, int64_t l
     __syncthreads();
     int status = 0, bad = k;
     for (int i = 0; i < k; ++i) {
+        // two barriers per column: the pivot is read by everybody BEFORE the barrier that precedes its
+        // overwrite (the diagonal entry is rewritten together with the trailing update, which never reads it)
         const double piv = T[i * lt + i];
         if (!(piv > 0.0)) { status = 1; bad = i; break; }
-        const double r = sqrt(piv);
+        const double rs = rsqrt(piv);
+        for (int c = i + 1 + tid; c < k; c += blockDim.x) T[i * lt + c] *= rs;
         __syncthreads();
-        for (int c = i + 1 + tid; c < k; c += blockDim.x) T[i * lt + c] /= r;
-        if (tid == 0) T[i * lt + i] = r;
-        __syncthreads();
+        if (tid == 0) T[i * lt + i] = piv * rs;
         for (int rr = i + 1 + ty; rr < k; rr += 32) {
             const double f = T[i * lt + rr];
             for (int cc = i + 1 + tx; cc < k; cc += 32)
@@ -582,11 +588,14 @@ chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int
     };
     for (int ii = 0; ii < ny; ++ii) {
         const int i = k + ii;
+        // first maximum of the diagonal: warp partials -> shared memory -> every warp folds them again
+        // (no broadcast barrier, no serial loop)
         double best = -1.0e308; int bj = ny;
         for (int j = ii + tid; j < ny; j += blockDim.x) {
             const double d = T[j * lt + j];
             if (d > best) { best = d; bj = j; }
         }
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ob = __shfl_xor_sync(0xffffffffu, best, o);
             const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
@@ -594,33 +603,38 @@ chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int
         }
         if (lane == 0) { red[warp] = best; redi[warp] = bj; }
         __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 32; ++w)
-                if (red[w] > best || (red[w] == best && redi[w] < bj)) { best = red[w]; bj = redi[w]; }
-            s_j = bj;
+        best = red[lane]; bj = redi[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
         }
-        __syncthreads();
-        const int j = s_j;
+        const int j = bj;
         if (j != ii && j < ny) {
+            // symmetric swap ii <-> j in one pass: rows and columns away from the 2 x 2 corner, the corner by
+            // one thread; the same two columns of U12 in global memory
             for (int c = tid; c < ny; c += blockDim.x) {
+                if (c == ii || c == j) continue;
                 const double a = T[ii * lt + c];
                 T[ii * lt + c] = T[j * lt + c];
                 T[j * lt + c] = a;
+                const double b = T[c * lt + ii];
+                T[c * lt + ii] = T[c * lt + j];
+                T[c * lt + j] = b;
             }
-            for (int r = tid; r < k; r += blockDim.x) {          // the same two columns of U12
+            if (tid == 0) {
+                const double dii = T[ii * lt + ii], djj = T[j * lt + j], dij = T[ii * lt + j], dji = T[j * lt + ii];
+                T[ii * lt + ii] = djj; T[j * lt + j] = dii; T[ii * lt + j] = dji; T[j * lt + ii] = dij;
+                const int t = ind[i]; ind[i] = ind[k + j]; ind[k + j] = t;
+            }
+            for (int r = tid; r < k; r += blockDim.x) {
                 const double a = A[(int64_t)r * ld + k + ii];
                 A[(int64_t)r * ld + k + ii] = A[(int64_t)r * ld + k + j];
                 A[(int64_t)r * ld + k + j] = a;
             }
-            __syncthreads();
-            for (int r = tid; r < ny; r += blockDim.x) {
-                const double a = T[r * lt + ii];
-                T[r * lt + ii] = T[r * lt + j];
-                T[r * lt + j] = a;
-            }
-            if (tid == 0) { const int t = ind[i]; ind[i] = ind[k + j]; ind[k + j] = t; }
-            __syncthreads();
         }
+        __syncthreads();                  // also fences red/redi against the next pivot search
         const double piv = T[ii * lt + ii];
         if (piv <= eps || !(piv > 0.0)) {
             __syncthreads();
@@ -631,14 +645,13 @@ chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int
             dropped = n - i;
             break;
         }
-        const double r = sqrt(piv);
-        __syncthreads();
+        const double rs = rsqrt(piv);
         for (int c = ii + 1 + tid; c < ny; c += blockDim.x) {
-            T[ii * lt + c] /= r;
+            T[ii * lt + c] *= rs;
             T[c * lt + ii] = 0.0;
         }
-        if (tid == 0) T[ii * lt + ii] = r;
         __syncthreads();
+        if (tid == 0) T[ii * lt + ii] = piv * rs;
         for (int rr = ii + 1 + ty; rr < ny; rr += 32) {
             const double f = T[ii * lt + rr];
             for (int cc = ii + 1 + tx; cc < ny; cc += 32) T[rr * lt + cc] = fma(-f, T[ii * lt + cc], T[rr * lt + cc]);

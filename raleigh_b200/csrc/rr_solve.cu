@@ -74,20 +74,20 @@ extern "C" {
 size_t rl_small_eigh_ws_bytes(int64_t n) { return n > 0 ? eigh_ws_bytes(n) : 0; }
 
 /* w, Q = eigh(sym(g)); device pointers; info_d (2 ints: sweeps, converged) may be NULL */
-int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double* w, double* q, int64_t ldq, void* ws,
+int rl_small_eigh(const double* g, int64_t ldg, int64_t n, double tol, double* w, double* q, int64_t ldq, void* ws,
                   size_t ws_bytes, int* info_d, void* stream) {
     if (n < 0) return RL_E_ARG;
     if (ws_bytes < rl_small_eigh_ws_bytes(n)) return RL_E_WORKSPACE;
-    return small_eigh(g, ldg, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream));
+    return small_eigh(g, ldg, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream), 0, tol);
 }
 
 /* w, Q = eigh(u^T u) from the upper Cholesky factor u (Jacobi on the factor: relative accuracy for every
  * eigenvalue); n <= rl_syevj_grid_max_n() */
-int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double* w, double* q, int64_t ldq, void* ws,
-                         size_t ws_bytes, int* info_d, void* stream) {
+int rl_small_eigh_factor(const double* u, int64_t ldu, int64_t n, double tol, double* w, double* q, int64_t ldq,
+                         void* ws, size_t ws_bytes, int* info_d, void* stream) {
     if (n < 0 || n > rl_syevj_grid_max_n()) return RL_E_ARG;
     if (ws_bytes < rl_small_eigh_ws_bytes(n)) return RL_E_WORKSPACE;
-    return small_eigh(u, ldu, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream), 1);
+    return small_eigh(u, ldu, n, w, q, ldq, ws, ws_bytes, info_d, as_stream(stream), 1, tol);
 }
 
 size_t rl_rr_solve_ws_bytes(int64_t nmax) {

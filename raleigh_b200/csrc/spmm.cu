@@ -244,11 +244,6 @@ static int spmm_launch(int64_t nrows, const int64_t* indptr, const int32_t* indi
     return check_launch();
 }
 
-// spmm_win.cu (experimental, knob-gated)
-bool spmm_win_ok(int dtype, const void* x, int64_t ldx, int64_t nrows, int64_t m);
-int spmm_win(int dtype, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
-             const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, cudaStream_t st);
-
 template <typename T>
 static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
                      const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int ncols_local, const void* halo,
@@ -258,9 +253,7 @@ static int spmm_impl(int64_t nrows, int64_t nnz, const int64_t* indptr, const in
     int64_t avg = nrows > 0 ? (nnz * 32 + nrows - 1) / nrows : 0;
     int64_t want = (avg * 5 / 4 + 63) / 64 * 64;            // 25 % head room over the average 32-row segment
     int cap = (int)(want < 256 ? 256 : want > 4096 ? 4096 : want);
-    if (g_knob[KNOB_SPMM_WINDOW] == 1 && halo == nullptr && run_order == nullptr &&
-        spmm_win_ok(sizeof(T) == 8 ? RL_F64 : RL_F32, x, ldx, nrows, m))
-        return spmm_win(sizeof(T) == 8 ? RL_F64 : RL_F32, nrows, nnz, indptr, indices, values, x, ldx, y, ldy, m, st);
+
     if (warps <= 0) warps = g_spmm_warps;
     // big CTAs only when the staged entries of all their warps leave most of L1 free
     if (warps >= 8 && (size_t)warps * cap * (sizeof(T) + 4) > 96 * 1024) warps = 4;

@@ -29,8 +29,10 @@ from .vectors import Vectors, block_gemm
 class _Work:
     """fp64 device workspace for one nsv x nsv factorisation."""
 
-    def __init__(self, n):
+    def __init__(self, n, dtype):
         self.n = n
+        # Jacobi stopping tolerance: working precision for fp64 data; fp32 Gram matrices carry 1e-7 noise
+        self.tol = 1e-9 if numpy.dtype(dtype) == numpy.float32 else 0.0
         ews = lib.rl_small_eigh_ws_bytes(n)
         mat = n * n * 8
         self.buf = dev.Buffer(5 * mat + 4 * n * 8 + ews + 4096, zero=True)
@@ -61,8 +63,8 @@ def _gram64(block, work):
 
 
 def _eigh(work, src):
-    check(lib.rl_small_eigh(src, work.n, work.n, work.w, work.Q, work.n, work.ews, work.ews_bytes, work.info,
-                            dev.stream()))
+    check(lib.rl_small_eigh(src, work.n, work.n, work.tol, work.w, work.Q, work.n, work.ews, work.ews_bytes,
+                            work.info, dev.stream()))
 
 
 def _factor(work):
@@ -85,7 +87,8 @@ def _eigh_gram(work, factored=None):
     if factored is None:
         factored = _factor(work)
     if factored:
-        check(lib.rl_small_eigh_factor(work.S, n, n, work.w, work.Q, n, work.ews, work.ews_bytes, work.info, st))
+        check(lib.rl_small_eigh_factor(work.S, n, n, work.tol, work.w, work.Q, n, work.ews, work.ews_bytes, work.info,
+                                       st))
     else:
         _eigh(work, work.G)
 
@@ -118,7 +121,7 @@ def finalize_svd(v, Av, eps):
     """Drop-in for PartialSVD._finalize_svd(v, Av, eps) on raleigh_b200 vectors."""
     nsv = v.nvec()
     dtype = v.data_type()
-    work = _Work(nsv)
+    work = _Work(nsv, dtype)
     st = dev.stream
     _gram64(Av, work)
 

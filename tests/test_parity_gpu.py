@@ -131,7 +131,8 @@ def test_error_behaviour(gpu_backend):
 
 
 @pytest.mark.parametrize('dtype', [np.float64, np.float32])
-@pytest.mark.parametrize('M,N,k', [(5, 7, 3), (64, 64, 64), (130, 257, 17), (1000, 333, 128), (257, 1024, 128)])
+@pytest.mark.parametrize('M,N,k', [(5, 7, 3), (64, 64, 64), (130, 257, 17), (1000, 333, 128), (257, 1024, 128),
+                                   (300, 517, 1), (1003, 2050, 2), (129, 4099, 7), (4000, 1024, 8), (67, 70, 1)])
 def test_dense_apply(gpu_backend, dtype, M, N, k):
     rng = np.random.RandomState(M + N)
     a = rng.randn(M, N).astype(dtype)
@@ -477,3 +478,28 @@ def test_spmm_halo_kernels_on_one_gpu(gpu_backend, dtype):
         check(lib.rl_sell_spmm_halo(code, nloc, slab.nnz, nsl, sp_.ptr, sc_.ptr, sv_.ptr, X._wptr(), X._ld,
                                     Y2._wptr(), Y2._ld, m, nloc, H.ptr, dev.stream()))
         close(Y2.data(), ref, dtype, scale)
+
+
+def test_dense_apply_skinny_at_config2_size(gpu_backend):
+    """k in {1, 2, 7} vectors against the 12,000 x 39,375 fp32 data matrix (the mean-shift vectors of the PCA
+    operator, partial_svd.py:256-277): the HBM-bound sweep of gemm_skinny.cu against fp64 NumPy on a row /
+    column sample, and linearity over the whole result."""
+    import torch
+    M, N = 12000, 39375
+    g = torch.Generator(device='cuda'); g.manual_seed(5)
+    a = torch.randn(M, N, generator=g, device='cuda', dtype=torch.float32)
+    A = gpu_backend.Matrix(a.cpu().numpy())
+    rng = np.random.RandomState(1)
+    for k in (1, 2, 7):
+        x = rng.randn(k, N).astype(np.float32)
+        X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(M, k, np.float32)
+        A.apply(X, Y)
+        ref = (torch.from_numpy(x).cuda().double() @ a.double().T).cpu().numpy()
+        got = Y.data()
+        assert np.max(np.abs(got - ref)) <= 3e-5 * np.sqrt(N) * max(1.0, np.max(np.abs(ref)) / np.sqrt(N))
+        z = rng.randn(k, M).astype(np.float32)
+        Z, W = gpu_backend.Vectors(z.copy()), gpu_backend.Vectors(N, k, np.float32)
+        A.apply(Z, W, transp=True)
+        ref = (torch.from_numpy(z).cuda().double() @ a.double()).cpu().numpy()
+        got = W.data()
+        assert np.max(np.abs(got - ref)) <= 3e-5 * np.sqrt(M) * max(1.0, np.max(np.abs(ref)) / np.sqrt(M))

@@ -140,7 +140,7 @@ def _eig(rt, G, fn='rl_syevj_cluster'):
         rt.check(rt.lib.rl_syevj_cluster(dG.data_ptr(), ld, n, 0, 0.0, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
                                          info.data_ptr(), rt.st()))
     else:
-        rt.check(getattr(rt.lib, fn)(dG.data_ptr(), ld, n, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
+        rt.check(getattr(rt.lib, fn)(dG.data_ptr(), ld, n, 0.0, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
                                      info.data_ptr(), rt.st()))
     return w.cpu().numpy(), Q.cpu().numpy(), info.cpu().numpy()
 
@@ -197,7 +197,7 @@ def test_potrf_and_jacobi_on_the_factor(rt, n, cond):
     w, Q = rt.zeros(n), rt.zeros(n, n)
     wsb = rt.lib.rl_small_eigh_ws_bytes(n)
     ws = rt.zeros(wsb // 8 + 8)
-    rt.check(rt.lib.rl_small_eigh_factor(dU.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
+    rt.check(rt.lib.rl_small_eigh_factor(dU.data_ptr(), n, n, 0.0, w.data_ptr(), Q.data_ptr(), n, ws.data_ptr(), wsb,
                                          info.data_ptr(), rt.st()))
     w, Q = w.cpu().numpy(), Q.cpu().numpy()
     assert int(info[1]) == 1, info.cpu().numpy()

@@ -230,22 +230,6 @@ def spmm_sweep(name, A_full, plans, reps):
                  sq_diff_vs_default=diff)
       lib.rl_debug_set_knob(KNOB_SPMM_WPS, 0)
       lib.rl_debug_set_knob(KNOB_SPMM_PF, 0)
-      if '--window' in sys.argv:            # experimental band-window kernel (spmm_win.cu), checked against the default
-          for chunks in (1, 4, 8):
-              lib.rl_debug_set_knob(KNOB_SPMM_WINDOW, 1)
-              lib.rl_debug_set_knob(KNOB_SPMM_WIN_CHUNKS, chunks)
-              f = lambda: check(lib.rl_csr_spmm_ex(1, n, nnz, ip.ptr, ix.ptr, va.ptr, X._wptr(), X._ld, Y._wptr(), Y._ld, m,
-                                                   0, None, None, 4, dev.stream()))
-              Y.zero()
-              f()
-              torch.cuda.synchronize()
-              check(lib.rl_axpy(1, Y._wptr(), Y._ld, Y0._wptr(), Y0._ld, m, n, -1.0, dev.stream()))
-              diff = float(np.abs(Y.dots(Y)).max())
-              ms, best = timeit(f, reps=reps)
-              emit(exp='spmm_window', matrix=name, n=n, nnz=nnz, m=m, chunks=chunks, ms=round(ms, 5), ms_best=round(best, 5),
-                   GBps=round(byts / ms / 1e6, 1), frac_hbm=round(byts / ms / 1e6 / peak_gbs(), 3), sq_diff_vs_default=diff)
-          lib.rl_debug_set_knob(KNOB_SPMM_WINDOW, 0)
-          lib.rl_debug_set_knob(KNOB_SPMM_WIN_CHUNKS, 0)
       if op.layout() == 'sell32':
         ms, best = timeit(lambda: op.apply(X, Y), reps=reps)
         emit(exp='spmm', matrix=name, n=n, nnz=nnz, m=m, group='sell32', ms=round(ms, 5), GBps=round(byts / ms / 1e6, 1),

@@ -85,7 +85,7 @@ def main():
         res = {}
         for p in (m, n):
             def eig():
-                check(lib.rl_small_eigh(G.data_ptr(), n, p, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+                check(lib.rl_small_eigh(G.data_ptr(), n, p, 0.0, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
             res['eigh_%d_ms' % p] = round(timeit(eig, 10), 4)
             res['eigh_%d_sweeps' % p] = int(info[0])
         B = up(rng.randn(n, n))
@@ -120,12 +120,12 @@ def big(emit):
         t_potrf = timeit(potrf, 5)
 
         def fac():
-            check(lib.rl_small_eigh_factor(U.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+            check(lib.rl_small_eigh_factor(U.data_ptr(), n, n, 0.0, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
         t_fac = timeit(fac, 3)
         sw_fac = int(info[0])
 
         def sym():
-            check(lib.rl_small_eigh(G.data_ptr(), n, n, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
+            check(lib.rl_small_eigh(G.data_ptr(), n, n, 0.0, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
         t_sym = timeit(sym, 3)
         emit(order=n, potrf_ms=round(t_potrf, 3), eigh_factor_ms=round(t_fac, 3), eigh_factor_sweeps=sw_fac,
              eigh_sym_ms=round(t_sym, 3), eigh_sym_sweeps=int(info[0]))
