@@ -371,6 +371,9 @@ int rl_psvd_coeffs(const double* qin, int64_t ldq, const double* w, int64_t n, d
  * with G = U^T U and S = D^-1/2 G D^-1/2,  lambda_min(S) >= 1 / sum_ij d_i (U^-1)_ij^2.
  * rl_small_set_identity: a = I;  rl_psvd_invbound: out[0] = sum_ij g_ii uinv_ij^2 */
 int rl_small_set_identity(double* a, int64_t ld, int64_t n, void* stream);
+/* dst[r][c] = src[r][c] * s[c] */
+int rl_small_scale_cols(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* s,
+                        double* dst, int64_t ldd, void* stream);
 int rl_psvd_invbound(const double* uinv, int64_t ldu, const double* g, int64_t ldg, int64_t n,
                      double* out, void* stream);
 

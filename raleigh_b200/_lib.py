@@ -110,6 +110,7 @@ PROTOTYPES = {
     'rl_syevj_grid_max_n': (c_int, []),
     'rl_syevj_cluster': (c_int, [c_vp, c_i64, c_i64, c_int, c_dbl, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
     'rl_small_set_identity': (c_int, [c_vp, c_i64, c_i64, c_vp]),
+    'rl_small_scale_cols': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     'rl_psvd_invbound': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     'rl_small_eigh_factor': (c_int, [c_vp, c_i64, c_i64, c_dbl, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_vp]),
     'rl_small_potrf': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),

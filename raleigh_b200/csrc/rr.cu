@@ -915,6 +915,14 @@ __global__ void psvd_scale_kernel(const double* __restrict__ G, int64_t ld, int 
             S[(int64_t)r * lds + c] = G[(int64_t)r * ld + c] / sqrt(fabs(G[(int64_t)r * ld + r] * G[(int64_t)c * ld + c]));
 }
 
+// dst[r][c] = src[r][c] * s[c]
+__global__ void small_scale_cols_kernel(const double* __restrict__ src, int64_t lds, int rows, int cols,
+                                        const double* __restrict__ sc, double* __restrict__ dst, int64_t ldd) {
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+            dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c] * sc[c];
+}
+
 __global__ void small_identity_kernel(double* __restrict__ a, int64_t ld, int n) {
     for (int r = blockIdx.y; r < n; r += gridDim.y)
         for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
@@ -1281,6 +1289,15 @@ int rl_psvd_invbound(const double* uinv, int64_t ldu, const double* g, int64_t l
                      void* stream) {
     if (n <= 0) return RL_E_ARG;
     psvd_invbound_kernel<<<1, 1024, 0, as_stream(stream)>>>(uinv, ldu, g, ldg, (int)n, out);
+    return check_launch();
+}
+
+
+int rl_small_scale_cols(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* s, double* dst,
+                        int64_t ldd, void* stream) {
+    if (rows < 0 || cols < 0) return RL_E_ARG;
+    if (rows == 0 || cols == 0) return 0;
+    small_scale_cols_kernel<<<small_grid((int)rows, (int)cols), 128, 0, as_stream(stream)>>>(src, lds, (int)rows, (int)cols, s, dst, ldd);
     return check_launch();
 }
 

@@ -44,11 +44,13 @@ class _Work:
         self.ews, self.ews_bytes = p + 4 * n * 8, ews
 
 
-def _gram64(block, work):
-    """work.G = block block^T in fp64 (fp32 blocks: tensor-core product, widened)."""
+def _gram64(block, work, exact=False):
+    """work.G = block block^T in fp64.  fp32 blocks: tensor-core product (3xTF32, fp32 accumulation: what the
+    reference's sgemm delivers), widened -- unless `exact`, which accumulates the exact fp32 products in fp64
+    (Vectors.svd needs singular values far below sqrt(eps_32) sigma_max)."""
     n = work.n
     st = dev.stream()
-    if block._code == 0 and n >= 48:
+    if block._code == 0 and n >= 48 and not exact:
         t = Vectors._local(n, n, block.data_type())
         block_gemm(block._code, block._wptr(), block._ld, n, block._n, block._wptr(), block._ld, t._wptr(), t._ld, n, 0)
         if block._shard is not None:

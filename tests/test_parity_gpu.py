@@ -503,3 +503,40 @@ def test_dense_apply_skinny_at_config2_size(gpu_backend):
         ref = (torch.from_numpy(z).cuda().double() @ a.double()).cpu().numpy()
         got = W.data()
         assert np.max(np.abs(got - ref)) <= 3e-5 * np.sqrt(M) * max(1.0, np.max(np.abs(ref)) / np.sqrt(M))
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('case', ['cond1e10', 'rank_deficient', 'zero_rows', 'graded'])
+def test_svd_returns_a_full_orthonormal_set(gpu_backend, dtype, case):
+    """Vectors.svd() on ill-conditioned and rank-deficient blocks (the situations in which the reference calls
+    it: partial_svd.py:183 `icond < 100 eps`, the restart at solver.py:885): S_new must have ORTHONORMAL rows --
+    numpy.linalg.svd always returns them -- and S_old = v diag(sigma) S_new must hold."""
+    rng = np.random.RandomState(11)
+    m, n = 24, 3000
+    u, _ = np.linalg.qr(rng.randn(m, m))
+    w, _ = np.linalg.qr(rng.randn(n, m))
+    big = dtype is np.float64
+    if case == 'cond1e10':
+        sig = np.logspace(0, -10 if big else -5, m)
+    elif case == 'rank_deficient':
+        sig = np.concatenate((np.linspace(1, 0.1, m - 7), np.zeros(7)))
+    elif case == 'zero_rows':
+        sig = np.linspace(1, 0.5, m)
+    else:
+        sig = np.logspace(0, -6 if big else -3, m)
+    s = ((u * sig) @ w.T).astype(dtype)
+    if case == 'zero_rows':
+        s[3] = 0
+        s[17] = 0
+    S = gpu_backend.Vectors(s.copy())
+    sigma, v = S.svd()
+    snew = S.data().astype(np.float64)
+    eps = np.finfo(dtype).eps
+    assert np.max(np.abs(snew @ snew.T - np.eye(m))) < 50 * m * eps, case
+    recon = (v.astype(np.float64) * sigma.astype(np.float64)[None, :]) @ snew
+    assert np.max(np.abs(recon - s)) < 50 * m * eps * max(1.0, np.max(np.abs(s)))
+    assert np.all(np.diff(sigma) <= 1e-6 * sigma[0])
+    exact = np.linalg.svd(s.astype(np.float64), compute_uv=False)
+    live = exact > (1e-9 if big else 3e-4) * exact[0]
+    assert np.max(np.abs(sigma[live] - exact[live]) / exact[live]) < (1e-6 if big else 2e-3)
+    assert np.max(np.abs(v.astype(np.float64).T @ v.astype(np.float64) - np.eye(m))) < 100 * m * eps

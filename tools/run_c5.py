@@ -44,12 +44,11 @@ prof = profile.report()
 t = torch.as_tensor(trans, device='cuda'); c = torch.as_tensor(comps, device='cuda')
 ds = a - torch.as_tensor(mean, device='cuda').reshape(1, -1)
 ef = (torch.linalg.norm(t @ c - ds) / torch.linalg.norm(ds)).item()
-line = {'config': 'C5 (reduced): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (args.rows, args.cols, args.chunk, args.tol),
+line = {'config': 'C5 (single GPU): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (args.rows, args.cols, args.chunk, args.tol),
         'gpu_s': round(dt, 3), 'components': int(comps.shape[0]), 'pca_error_frobenius': ef,
         'device_ms': round(sum(v_['ms'] for v_ in prof.values()), 1),
         'kernels': {k: {'count': v_['count'], 'ms': round(v_['ms'], 1)} for k, v_ in prof.items()}}
 if args.cpu:
-    from bench import load_reference_cpu
     np.random.seed(1)
     t0 = time.perf_counter()
     mean2, trans2, comps2 = pca(A, tol=args.tol, batch_size=args.chunk, arch='cpu', opt=Options())

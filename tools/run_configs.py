@@ -5,9 +5,10 @@ same inputs / seeds / solver options:
   C3: synthetic shipsec1-shaped SPD CSR (140,874 rows, ~55 nnz/row, fp64), 10 smallest,
       Jacobi preconditioning, block 32 -- through partial_hevp(A, T=...)
 
-Both sides run the reference's UNMODIFIED core solver; the CPU side uses the oracle port
-of the reference's NumPy algebra (MKL is absent).  Prints one JSON line per config:
-times, iteration counts side by side, max relative eigenvalue difference, residuals.
+Three arms on the same inputs: the device-resident driver (raleigh_b200/jcg.py, default), the
+reference's UNMODIFIED main loop on the same GPU backend (verbatim path), and the reference solver on
+the oracle port of its NumPy algebra on the host (MKL is absent).  Prints one JSON line per config:
+times, iteration counts side by side, max relative eigenvalue differences, residuals.
 
     python tools/run_configs.py [c1] [c3] [--tol 1e-6] [--no-cpu]
 """
@@ -56,10 +57,25 @@ def solve(Vectors, op, n, dtype, nev, tol, block, T=None, max_iter=2000):
                 lmd=np.sort(np.array(solver.eigenvalues)), x=v)
 
 
-def report(name, A, gpu, cpu, extra):
+def both(fn):
+    """(device-resident driver, verbatim main loop) on the GPU backend."""
+    rb.use_device_solver(False)
+    try:
+        verb = fn()
+    finally:
+        rb.use_device_solver(True)
+    return fn(), verb
+
+
+def report(name, A, gpu, cpu, extra, verb=None):
     lmd = gpu['lmd']
     line = {'config': name, 'gpu_s': round(gpu['seconds'], 4), 'gpu_iterations': gpu['iterations'],
             'gpu_status': gpu['status'], 'eigenvalues': [float(t) for t in lmd[:10]]}
+    if verb is not None:
+        k = min(len(lmd), len(verb['lmd']))
+        line.update({'gpu_verbatim_s': round(verb['seconds'], 4), 'gpu_verbatim_iterations': verb['iterations'],
+                     'max_rel_eigenvalue_diff_device_vs_verbatim':
+                     float(np.max(np.abs(lmd[:k] - verb['lmd'][:k]) / np.abs(verb['lmd'][:k])))})
     line.update(extra)
     if cpu is not None:
         k = min(len(lmd), len(cpu['lmd']))
@@ -92,12 +108,12 @@ def main():
             n = L.shape[0]
             op = rb.SparseSymmetricMatrix(L)
             solve(rb.Vectors, op, n, np.float64, 10, tol, -1)            # warm-up (allocator, module load)
-            gpu = solve(rb.Vectors, op, n, np.float64, 10, tol, -1)
+            gpu, verb = both(lambda: solve(rb.Vectors, op, n, np.float64, 10, tol, -1))
             cpu = solve(oracle.Vectors, oracle.SparseSymmetricMatrix(L), n, np.float64, 10, tol, -1) if do_cpu else None
             exact = K.lap3d_eigenvalues(32, 32, 32)[:10]
             out.append(report('C1 lap3d 32^3, 10 smallest, tol %g, block auto' % tol, L, gpu, cpu, {
                 'n': n, 'nnz': int(L.nnz), 'max_rel_err_vs_analytic': float(np.max(np.abs(gpu['lmd'] - exact) / exact)),
-                'max_rel_residual': residuals(L, gpu), 'spmm_layout': op.layout()}))
+                'max_rel_residual': residuals(L, gpu), 'spmm_layout': op.layout()}, verb))
         if 'c3' in which:
             from raleigh.interfaces.partial_hevp import partial_hevp
             n = 140874
@@ -105,14 +121,15 @@ def main():
             op = rb.SparseSymmetricMatrix(A)
             T = rb.Operator(rb.DiagonalPreconditioner(A))
             solve(rb.Vectors, op, n, np.float64, 10, 1e-2, 32, T=T)     # warm-up
-            gpu = solve(rb.Vectors, op, n, np.float64, 10, tol, 32, T=T)
+            gpu, verb = both(lambda: solve(rb.Vectors, op, n, np.float64, 10, tol, 32, T=T))
             cpu = None
             if do_cpu:
                 cpu = solve(oracle.Vectors, oracle.SparseSymmetricMatrix(A), n, np.float64, 10, tol, 32,
                             T=oracle.Operator(oracle.Jacobi(A)))
             line = report('C3 synthetic SPD n=140874 (~%d nnz/row), 10 smallest, Jacobi, block 32, tol %g'
                           % (A.nnz // n, tol), A, gpu, cpu, {
-                              'n': n, 'nnz': int(A.nnz), 'max_rel_residual': residuals(A, gpu), 'spmm_layout': op.layout()})
+                              'n': n, 'nnz': int(A.nnz), 'max_rel_residual': residuals(A, gpu), 'spmm_layout': op.layout()},
+                          verb)
             # the same through the reference's partial_hevp entry point (preconditioned branch)
             np.random.seed(1)
             opt = rs.Options()
