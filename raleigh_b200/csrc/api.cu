@@ -82,8 +82,19 @@ std::mutex g_mu;
 constexpr size_t kRingDefault = size_t(8) << 20;
 }  // namespace
 
+// The ring and the scratch belong to ONE device (the one current at first use) and rely on stream order for
+// reuse: a call arriving with another device current would get pointers into the wrong address space.
+static int g_owner_device = -1;
+static int check_owner_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RL_E_ARG;
+    if (g_owner_device < 0) g_owner_device = dev;
+    return dev == g_owner_device ? 0 : RL_E_ARG;
+}
+
 int staging_acquire(size_t bytes, void** pinned, void** dev) {
     std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = check_owner_device()) return rc;
     bytes = (bytes + 255) & ~size_t(255);
     if (bytes == 0) bytes = 256;
     if (g_ring.cap < 2 * bytes || g_ring.pinned == nullptr) {
@@ -110,6 +121,7 @@ int staging_acquire(size_t bytes, void** pinned, void** dev) {
 
 int scratch_acquire(size_t bytes, void** dev) {
     std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = check_owner_device()) return rc;
     if (g_scratch.cap < bytes || g_scratch.dev == nullptr) {
         size_t want = g_scratch.cap ? g_scratch.cap : (size_t(4) << 20);
         while (want < bytes) want *= 2;

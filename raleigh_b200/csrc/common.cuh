@@ -20,12 +20,13 @@ extern int64_t g_launches;          // kernels launched by this library (api.cu)
 //  (knobs 6, 7: the r1 band-window SpMM experiment, measured 0.60 vs 0.33 ms on the 128^3 stencil in r2a and removed;
 //   profiles/r2a_sweep_spmm_window.jsonl)
 //  GEMM_INSPLIT: 1 = experimental in-kernel lo split of the tcgen05 dense apply (gemm_tc.cu)
+//  CHOL_NOEST: 1 = (measurements only) pivoted Cholesky without the condition estimates of the drop rule;
 //  GEMM_SKINNY: -1 = dense applies with k <= 8 vectors stay on the tiled FMA kernel (gemm_simt.cu);
 //  BLOCK_TC: -1 = fp32 Gram / block update of the device-resident driver never on the tensor cores;
 //  CHOL_GLOBAL: 1 = pivoted Cholesky always in global memory (the shared-memory split is the default);
 //  EIG_LEGACY: 1 = always use the cooperative-grid two-sided Jacobi kernel (small.cu) instead of the cluster kernel
 enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_SPMM_WINDOW = 6, KNOB_SPMM_WIN_CHUNKS = 7, KNOB_GEMM_INSPLIT = 8,
-            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_GEMM_SKINNY = 12, KNOB_COUNT = 16 };
+            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_GEMM_SKINNY = 12, KNOB_CHOL_NOEST = 13, KNOB_COUNT = 16 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 

@@ -29,27 +29,25 @@ namespace rl {
 constexpr int JC_MAX_SWEEPS = 48;
 constexpr int JC_MAX_CLUSTER = 8;
 
-// sigma and the convergence tolerance; one CTA
+// sigma from the Gershgorin discs of sym(G); one CTA, one warp per row (coalesced row reads)
 __global__ void __launch_bounds__(1024)
 jacobi_shift_kernel(const double* __restrict__ G, int64_t ld, int n, double* __restrict__ par) {
     __shared__ double rlo[32], rhi[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double lo = 1.0e308, hi = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = warp; i < n; i += nw) {
         double rad = 0.0;
-        for (int j = 0; j < n; ++j)
+        for (int j = lane; j < n; j += 32)
             if (j != i) rad += fabs(0.5 * (G[(int64_t)i * ld + j] + G[(int64_t)j * ld + i]));
+        rad = warp_sum(rad);
         const double d = G[(int64_t)i * ld + i];
         lo = fmin(lo, d - rad);
         hi = fmax(hi, fabs(d) + rad);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) { rlo[threadIdx.x >> 5] = lo; rhi[threadIdx.x >> 5] = hi; }
+    if (lane == 0) { rlo[warp] = lo; rhi[warp] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, rlo[w]); hi = fmax(hi, rhi[w]); }
+        for (int w = 1; w < nw; ++w) { lo = fmin(lo, rlo[w]); hi = fmax(hi, rhi[w]); }
         double sigma = 0.0;
         if (lo <= 1e-3 * hi) sigma = -lo + 1e-2 * hi;     // not safely positive definite: shift
         if (!(hi > 0.0)) sigma = 1.0;                      // zero matrix: B = I
@@ -294,7 +292,7 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
         for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
         nrm = sqrt(nrm);
         const bool real_col = nrm > 0.0;
-        if (lane == 0) wtmp[slot] = real_col ? (factor_mode ? nrm * nrm : nrm - sigma) : 1.0e308;   // padding columns sort last
+        if (lane == 0) wtmp[slot] = real_col ? (factor_mode ? nrm * nrm : nrm - sigma) : (double)INFINITY;   // resolved by the sort kernel
         const double inv = real_col ? 1.0 / nrm : 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -306,15 +304,31 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
     if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = converged; }
 }
 
-// ascending order: w[rank] = value, Q[r][rank] = qtmp[slot][r]; every CTA ranks all slots, then scatters its share
+// ascending order: w[rank] = value, Q[r][rank] = qtmp[slot][r]; every CTA ranks all slots, then scatters its share.
+// Columns of zero norm arrive marked +inf: the first (slots - n) of them in slot order are the padding columns,
+// any further ones are genuine null directions of a singular matrix and get `zero_value` (their eigenvector
+// columns stay zero: the caller completes the basis).
 __global__ void __launch_bounds__(1024)
 jacobi_sort_kernel(const double* __restrict__ wtmp, const double* __restrict__ qtmp, int slots, int len, int n,
-                   double* __restrict__ w, double* __restrict__ Q, int64_t ldq) {
-    extern __shared__ int s_rank[];
+                   double zero_value, double* __restrict__ w, double* __restrict__ Q, int64_t ldq) {
+    extern __shared__ __align__(8) unsigned char js_smem[];
+    double* vals = reinterpret_cast<double*>(js_smem);               // [slots]
+    int* s_rank = reinterpret_cast<int*>(vals + slots);              // [slots]
+    const int npad = slots - n;
     for (int i = threadIdx.x; i < slots; i += blockDim.x) {
-        const double v = wtmp[i];
+        double v = wtmp[i];
+        if (isinf(v)) {
+            int before = 0;
+            for (int j = 0; j < i; ++j) before += isinf(wtmp[j]) ? 1 : 0;
+            v = before < npad ? 1.0e308 : zero_value;
+        }
+        vals[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < slots; i += blockDim.x) {
+        const double v = vals[i];
         int r = 0;
-        for (int j = 0; j < slots; ++j) { const double u = wtmp[j]; r += (u < v) || (u == v && j < i); }
+        for (int j = 0; j < slots; ++j) { const double u = vals[j]; r += (u < v) || (u == v && j < i); }
         s_rank[i] = r;
         if (r < n && blockIdx.x == 0) w[r] = v;
     }
@@ -328,8 +342,6 @@ jacobi_sort_kernel(const double* __restrict__ wtmp, const double* __restrict__ q
         __syncthreads();
         if (s0 + ty < slots && r0 + tx < n) tile[ty][tx] = qtmp[(size_t)(s0 + ty) * len + r0 + tx];
         __syncthreads();
-        // thread (ty, tx): row r0 + ty, slot s0 + tx -> column rank[slot]; ranks of neighbouring slots are not
-        // contiguous in general, but after convergence they mostly are (nearly sorted columns)
         if (s0 + tx < slots && r0 + ty < n) {
             const int c = s_rank[s0 + tx];
             if (c < n) Q[(int64_t)(r0 + ty) * ldq + c] = tile[tx][ty];
@@ -515,7 +527,7 @@ static int syevj_grid(const double* g, int64_t ldg, int64_t n, int factor_mode, 
     jacobi_grid_finish_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(bt, len, (int)n, factor_mode, par, wtmp);
     rc = check_launch();
     if (rc) return rc;
-    jacobi_sort_kernel<<<(unsigned)(n >= 512 ? 64 : 8), 1024, (size_t)n * sizeof(int), st>>>(wtmp, bt, (int)n, (int)len, (int)n, w, q, ldq);
+    jacobi_sort_kernel<<<(unsigned)(n >= 512 ? 64 : 8), 1024, (size_t)n * 12, st>>>(wtmp, bt, (int)n, (int)len, (int)n, 0.0, w, q, ldq);
     return check_launch();
 }
 
@@ -572,7 +584,7 @@ int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, int factor_mode, d
         default: return RL_E_ARG;
     }
     if (rc) return rc;
-    jacobi_sort_kernel<<<(unsigned)(n >= 128 ? 8 : 1), 1024, (size_t)slots * sizeof(int), st>>>(wtmp, qtmp, slots, len, (int)n, w, q, ldq);
+    jacobi_sort_kernel<<<(unsigned)(n >= 128 ? 8 : 1), 1024, (size_t)slots * 12, st>>>(wtmp, qtmp, slots, len, (int)n, 0.0, w, q, ldq);
     return check_launch();
 }
 

@@ -561,7 +561,7 @@ chol_lead_smem_kernel(double* __restrict__ A, double* __restrict__ A0, int64_t l
 
 __global__ void __launch_bounds__(CH_THREADS)
 chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int64_t ld, int n, int k, double eps,
-                      int* __restrict__ ind, int* __restrict__ info) {
+                      int* __restrict__ ind, int* __restrict__ info, int no_estimates) {
     __shared__ double red[32];
     __shared__ int redi[32];
     __shared__ double tile[32][33];
@@ -657,7 +657,7 @@ chol_tail_smem_kernel(double* __restrict__ A, const double* __restrict__ A0, int
             for (int cc = ii + 1 + tx; cc < ny; cc += 32) T[rr * lt + cc] = fma(-f, T[ii * lt + cc], T[rr * lt + cc]);
         }
         __syncthreads();
-        if (i - l == blk - 1 || i == n - 1) {
+        if (!no_estimates && (i - l == blk - 1 || i == n - 1)) {
             last_check = i;
             flush(ii + 1);
             const double ratio = cond_inverse(A, A0, ld, i + 1, ind, vec, tile, part, red);
@@ -1181,7 +1181,7 @@ int rl_rr_piv_chol(double* a, double* a0, int64_t ld, int64_t n, int64_t k, doub
             if (rc) return rc;
         }
         const size_t smem = (size_t)(((n + 1) & ~int64_t(1)) + ny * (ny + 1)) * sizeof(double);
-        chol_tail_smem_kernel<<<1, CH_THREADS, smem, st>>>(a, a0, ld, (int)n, (int)k, eps, ind, info);
+        chol_tail_smem_kernel<<<1, CH_THREADS, smem, st>>>(a, a0, ld, (int)n, (int)k, eps, ind, info, g_knob[KNOB_CHOL_NOEST] == 1);
         return check_launch();
     }
     piv_chol_kernel<<<1, CH_THREADS, (size_t)n * sizeof(double), st>>>(a, a0, ld, (int)n, (int)k, eps, ind, info);

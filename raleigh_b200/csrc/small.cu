@@ -132,7 +132,7 @@ syevj_smem_kernel(double* __restrict__ Ag, int p, double* __restrict__ w, double
     }
     __syncthreads();
     for (int e = tid; e < p * p; e += nt) Ag[(e / p) * p + perm[e % p]] = V[e];
-    if (tid == 0) *sweeps_out = sweep;
+    if (tid == 0) *sweeps_out = sweep >= EIG_MAX_SWEEPS ? -2 : sweep;     // -2: sweeps exhausted without convergence
 }
 
 // ---- cooperative multi-CTA kernel, A and V in global memory (L2) ----------------------
@@ -217,7 +217,7 @@ syevj_coop_kernel(double* __restrict__ A, int p, double* __restrict__ w, double*
     }
     grid.sync();
     for (int64_t e = gtid; e < (int64_t)p * p; e += gnt) A[(e / p) * p + __ldcg(perm + e % p)] = __ldcg(V + e);
-    if (gtid == 0) *sweeps_out = sweep;
+    if (gtid == 0) *sweeps_out = sweep >= EIG_MAX_SWEEPS ? -2 : sweep;
 }
 
 }  // namespace rl

@@ -351,7 +351,13 @@ int rl_update(int dtype, void* out, int64_t ldo, int64_t m, const void* x, int64
         else scale_all_kernel<double><<<g, 256, 0, st>>>((double*)out, ldo, m, n, beta);
         return check_launch();
     }
-    if (out == x) return RL_E_ALIAS;
+    {   // Out must not overlap X: compare the byte ranges of the two windows, not just the base pointers
+        // (select() sub-blocks and shallow references of one buffer; NumPy materialises a temporary)
+        const size_t w = dtype == RL_F32 ? 4 : 8;
+        const char* o0 = (const char*)out; const char* o1 = o0 + ((size_t)(m - 1) * ldo + n) * w;
+        const char* x0 = (const char*)x;   const char* x1 = x0 + ((size_t)(k - 1) * ldx + n) * w;
+        if (o0 < x1 && x0 < o1) return RL_E_ALIAS;
+    }
     Span span(PK_UPDATE, st, (1.0 * k + (beta != 0.0 ? 2.0 : 1.0) * m) * n * (dtype == RL_F32 ? 4 : 8),
               2.0 * n * k * m);
     if (dtype == RL_F32) return update_impl<float>(out, ldo, m, x, ldx, k, q, q_rs, q_cs, alpha, beta, n, st);

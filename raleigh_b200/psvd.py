@@ -34,14 +34,15 @@ class _Work:
         # Jacobi stopping tolerance: working precision for fp64 data; fp32 Gram matrices carry 1e-7 noise
         self.tol = 1e-9 if numpy.dtype(dtype) == numpy.float32 else 0.0
         ews = lib.rl_small_eigh_ws_bytes(n)
-        mat = n * n * 8
-        self.buf = dev.Buffer(5 * mat + 4 * n * 8 + ews + 4096, zero=True)
-        p = self.buf.ptr
+        mat = (n * n * 8 + 255) & ~255                 # every piece 256-byte aligned (128-bit accesses in the kernels)
+        vec = (n * 8 + 255) & ~255
+        self.buf = dev.Buffer(5 * mat + 4 * vec + ews + 4096, zero=True)
+        p = (self.buf.ptr + 255) & ~255
         self.G, self.S, self.Q, self.q, self.cs = (p + i * mat for i in range(5))
         p += 5 * mat
-        self.w, self.sigma, self.ger = p, p + n * 8, p + 2 * n * 8
-        self.info = p + 3 * n * 8
-        self.ews, self.ews_bytes = p + 4 * n * 8, ews
+        self.w, self.sigma, self.ger = p, p + vec, p + 2 * vec
+        self.info = p + 3 * vec
+        self.ews, self.ews_bytes = p + 4 * vec, ews
 
 
 def _gram64(block, work, exact=False):

@@ -350,6 +350,11 @@ class Vectors:
             check(lib.rl_dots_t(self._code, self._wptr(), self._ld, other._wptr(), other._ld, m, n, out.ptr,
                                 dev.stream()))
             check(lib.rl_d2h(dev.host_ptr(w), out.ptr, n * self._w, dev.stream()))
+            if self._shard is not None:
+                # one entry per COMPONENT: a row-sharded block owns a slice of the result; callers
+                # (truncated_svd.py:183-197, lra.py:321) index it with the global dimension
+                ctx = self._shard[0]
+                w = ctx.allgather_columns(w.reshape(1, -1), ctx.allgather_counts(n)).reshape(-1)
             return w
         w = numpy.zeros((m,), dtype=self._dtype)
         if m < 1:
@@ -678,8 +683,13 @@ class Matrix:
         dev.upload_2d(self._aptr(), self._ld * self._w, numpy.ascontiguousarray(stored, dtype=self._dtype))
 
     def dots(self):
+        """Squared 2-norms of the rows, one per row of the LOGICAL matrix (dense_numpy.py:177-179)."""
         v = Vectors(self, shallow=True)
-        return v.dots(v)
+        w = v.dots(v)
+        if self._mshard is not None:        # this process holds a row slab: concatenate the slabs' results
+            ctx = self._mshard[0]
+            w = ctx.allgather_columns(w.reshape(1, -1), ctx.allgather_counts(w.shape[0])).reshape(-1)
+        return w
 
     def new_vectors(self, dim=None, nv=0):
         if dim is None:

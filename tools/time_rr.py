@@ -37,6 +37,8 @@ def up(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=None)
+    ap.add_argument('--blocks', default='16,32,64,120,128,160')
+    ap.add_argument('--no-big', action='store_true')
     args = ap.parse_args()
     out = open(args.out, 'w') if args.out else None
 
@@ -47,7 +49,7 @@ def main():
             out.write(line + '\n')
 
     st = dev.stream
-    for m in (16, 32, 64, 120, 128, 160):
+    for m in [int(t) for t in args.blocks.split(',') if t]:
         n = 2 * m
         rng = np.random.RandomState(m)
         N = 6 * n
@@ -67,6 +69,9 @@ def main():
             check(lib.rl_rr_piv_chol(dGB.data_ptr(), dA0.data_ptr(), n, n, m, 1e-8, ind.data_ptr(), info.data_ptr(), st()))
         t_chol = timeit(chol)
         assert int(info[0]) == 0
+        lib.rl_debug_set_knob(13, 1)           # the same without the condition estimates of the drop rule
+        t_chol_noest = timeit(chol)
+        lib.rl_debug_set_knob(13, 0)
         wsb = lib.rl_rr_solve_ws_bytes(n)
         ws = torch.zeros(wsb // 8 + 8, dtype=torch.float64, device='cuda')
         cx, cz = torch.zeros(n, n, dtype=torch.float64, device='cuda'), torch.zeros(n, n, dtype=torch.float64, device='cuda')
@@ -93,9 +98,10 @@ def main():
         def trsm():
             check(lib.rl_small_trsm(0, dGB.data_ptr(), n, n, B.data_ptr(), n, n, st()))
         t_trsm = timeit(trsm)
-        emit(block=m, nxy=n, piv_chol_ms=round(t_chol, 4), rr_solve_ms=round(t_rr, 4), rr_final_eigh_sweeps=sweeps_rr,
+        emit(block=m, nxy=n, piv_chol_ms=round(t_chol, 4), piv_chol_no_estimates_ms=round(t_chol_noest, 4), rr_solve_ms=round(t_rr, 4), rr_final_eigh_sweeps=sweeps_rr,
              trsm_ms=round(t_trsm, 4), **res)
-    big(emit)
+    if not args.no_big:
+        big(emit)
 
 
 def big(emit):
