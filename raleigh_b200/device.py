@@ -27,9 +27,20 @@ def require_cuda():
     _checked = True
 
 
+_device_index = None
+
+
 def stream():
-    """cudaStream_t of torch's current stream, as an int for ctypes."""
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream, as an int for ctypes.  Called once per C-ABI call (about 80
+    times per solver iteration): the raw query (0.3 us) instead of torch.cuda.current_stream() (15 us, profiled
+    at 15 ms per config-2 solve).  One process drives one device (dist.py), so its index is looked up once."""
+    global _device_index
+    if _device_index is None:
+        _device_index = torch.cuda.current_device()
+    try:
+        return torch._C._cuda_getCurrentRawStream(_device_index)
+    except AttributeError:          # private API moved: fall back to the public one
+        return torch.cuda.current_stream().cuda_stream
 
 
 def synchronize():

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 from threadpoolctl import threadpool_limits
 import raleigh_b200 as rb
-from bench import generate_c2
+from bench import generate_shard as generate_c2
 rb.install()
 from raleigh.interfaces.lra import LowerRankApproximation
 from raleigh.algebra.dense_matrix import AMatrix
@@ -22,4 +22,5 @@ with threadpool_limits(limits=1):
     solve()
     torch.cuda.synchronize(); t0 = time.time(); solve(); torch.cuda.synchronize(); print('solve s', time.time() - t0)
     pr = cProfile.Profile(); pr.enable(); solve(); pr.disable()
-st = pstats.Stats(pr); st.sort_stats('tottime').print_stats(18)
+st = pstats.Stats(pr); st.sort_stats('tottime').print_stats(28)
+st.sort_stats('cumulative').print_stats(30)
