@@ -21,6 +21,7 @@
 // cooperative-grid two-sided kernel in small.cu (measured r1e) and ~6 ms for LAPACK on the host.
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -450,6 +451,323 @@ __global__ void jacobi_grid_finish_kernel(double* __restrict__ bt, int64_t ldb, 
     if (lane == 0) wtmp[c] = nrm > 0.0 ? (factor_mode ? nrm * nrm : nrm - sigma) : (factor_mode ? 0.0 : -sigma);
 }
 
+// ---- 320 < n <= 1024, two-level tournament over the whole GPU (default) ------------------------------------------
+// The scheme of the cluster kernel with global memory (L2 resident, 16 MB at n = 1000) in place of distributed
+// shared memory: CTA c holds two blocks of RW = 8 columns; an outer round = (load both blocks into shared memory)
+// + RW inner rounds pairing A_w (registers of warp w) with B_(w+r) + (send A to CTA c+1, B to CTA c-1, into the
+// other half of a double buffer).  n-1 rotation rounds per sweep as before, but only 2C-1 ~ n/8 of them end
+// with an exchange, and the exchange is POINT-TO-POINT: a CTA waits for the two blocks it receives (one
+// release/acquire flag per block, written by the block's unique sender) instead of for the whole grid.  Every
+// CTA sends to exactly the CTAs it receives from, so a sender that has started round g has seen its
+// destinations' round g-1 messages, i.e. they are past their loads of the buffer half it overwrites.
+// One counting barrier per sweep carries the "anybody rotated" flag.  The launch is cooperative for the
+// co-residency guarantee only; every spin is bounded and watches a global abort word (info[1] = -1).
+constexpr int RW = 8;
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// thread 0 only; false = gave up (somebody aborted or the bound was hit)
+__device__ __forceinline__ bool ring_wait(const unsigned* flag, unsigned want, unsigned* abort_word) {
+    for (unsigned spin = 0; ld_acquire(flag) < want; ++spin) {
+        if ((spin & 1023u) == 1023u) {
+            if (ld_acquire(abort_word) != 0u) return false;
+            if (spin > (1u << 27)) { atomicExch(abort_word, 1u); return false; }
+        }
+    }
+    return true;
+}
+// both channels at once: the two polls travel together, ONE fence orders everything after them
+__device__ __forceinline__ bool ring_wait2(const unsigned* fa, const unsigned* fb, unsigned want, unsigned* abort_word) {
+    for (unsigned spin = 0;; ++spin) {
+        const unsigned a = ld_relaxed(fa), b = ld_relaxed(fb);
+        if (a >= want && b >= want) break;
+        if ((spin & 1023u) == 1023u) {
+            if (ld_relaxed(abort_word) != 0u) return false;
+            if (spin > (1u << 27)) { atomicExch(abort_word, 1u); return false; }
+        }
+    }
+    __threadfence();
+    return true;
+}
+
+// bulk (TMA, non-tensor) copies: one thread moves a whole block of columns between shared memory and L2
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+// sync words: flagA[C] | flagB[C] | barrier | abort | rotated[JC_MAX_SWEEPS]
+template <int NQ>
+__global__ void __launch_bounds__(RW * 32, 1)
+jacobi_ring_kernel(double* __restrict__ gbuf, int factor_mode, double tol, const double* __restrict__ par,
+                   unsigned* __restrict__ sync_words, double* __restrict__ wtmp, int* __restrict__ info, int dbg) {
+    extern __shared__ __align__(16) unsigned char jr_smem[];
+    constexpr int LEN = 64 * NQ;
+    constexpr int CH = LEN / 2;                                  // 16-byte chunks per column
+    double2* sm = reinterpret_cast<double2*>(jr_smem);           // [2 RW][CH]: A block, then B block
+    __shared__ int s_rot[RW];
+    __shared__ int s_ok, s_any;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_bn[RW];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rank = blockIdx.x, C = gridDim.x;
+    const size_t half_stride = (size_t)2 * RW * C * CH;          // double2 per half of the double buffer
+    double2* g2 = reinterpret_cast<double2*>(gbuf);
+    unsigned* flagA = sync_words;
+    unsigned* flagB = sync_words + C;
+    unsigned* bar = sync_words + 2 * C;
+    unsigned* abort_word = bar + 1;
+    unsigned* rotated = bar + 2;
+    const double tol2 = tol * tol;
+    const double sigma = factor_mode ? 0.0 : par[0];
+    constexpr uint32_t BLOCK_BYTES = RW * LEN * sizeof(double);  // one block of columns: 32 or 64 KB
+
+    int a_rank, a_side, b_rank, b_side;
+    if (rank == 0) { a_rank = 0; a_side = 0; b_rank = 1; b_side = 0; }
+    else {
+        if (rank == C - 1) { a_rank = rank; a_side = 1; } else { a_rank = rank + 1; a_side = 0; }
+        b_rank = rank - 1; b_side = 1;
+    }
+    if (dbg & 2) { a_rank = rank; a_side = 0; b_rank = rank; b_side = 1; }      // timing experiment: nothing moves
+    const size_t own = (size_t)rank * 2 * RW * CH;
+    const size_t dst_a = ((size_t)a_rank * 2 * RW + a_side * RW) * CH;
+    const size_t dst_b = ((size_t)b_rank * 2 * RW + b_side * RW) * CH;
+    unsigned* flag_a = (a_side ? flagB : flagA) + a_rank;
+    unsigned* flag_b = (b_side ? flagB : flagA) + b_rank;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nouter = 2 * C - 1;
+    unsigned g = 0;                                              // outer rounds done = messages sent per channel
+    int sweep = 0, converged = 0, aborted = 0;
+    for (; sweep < JC_MAX_SWEEPS && !aborted; ++sweep) {
+        int rot = 0;
+        for (int o = 0; o < nouter; ++o) {
+            // thread 0: wait for this round's two blocks, then pull them (contiguous: A block, B block) into shared memory
+            if (threadIdx.x == 0) {
+                int ok = 1;
+                if (g > 0) ok = ring_wait2(flagA + rank, flagB + rank, g, abort_word);
+                s_ok = ok;
+                if (ok) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    const double2* src = g2 + (g & 1u) * half_stride + own;
+                    mbar_expect_tx(&s_bar, 2 * BLOCK_BYTES);
+#pragma unroll
+                    for (int part = 0; part < 4; ++part)
+                        bulk_g2s(reinterpret_cast<unsigned char*>(sm) + part * (BLOCK_BYTES / 2),
+                                 reinterpret_cast<const unsigned char*>(src) + part * (BLOCK_BYTES / 2), BLOCK_BYTES / 2, &s_bar);
+                }
+            }
+            __syncthreads();
+            if (!s_ok) { aborted = 1; break; }
+            mbar_wait(&s_bar, g & 1u);
+            if (o == 0 && !(dbg & 1)) {
+                // pairs inside each block: circle method on RW players, 4 pairs per block = one per warp
+                for (int t = 0; t < RW - 1; ++t) {
+                    const int blk = w >> 2, i = w & 3;
+                    int a, b;
+                    if (i == 0) { a = RW - 1; b = t; } else { a = (t + i) % (RW - 1); b = (t - i + RW - 1) % (RW - 1); }
+                    double2* cp = sm + (size_t)(blk * RW + a) * CH;
+                    double2* cq = sm + (size_t)(blk * RW + b) * CH;
+                    double2 p[NQ], q[NQ];
+                    double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) {
+                        p[j] = cp[lane + 32 * j];
+                        q[j] = cq[lane + 32 * j];
+                        alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
+                        beta = fma(q[j].x, q[j].x, beta); beta = fma(q[j].y, q[j].y, beta);
+                        gamma = fma(p[j].x, q[j].x, gamma); gamma = fma(p[j].y, q[j].y, gamma);
+                    }
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                        alpha += __shfl_xor_sync(0xffffffffu, alpha, o2);
+                        beta += __shfl_xor_sync(0xffffffffu, beta, o2);
+                        gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
+                    }
+                    double c, s, tt;
+                    if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, tt)) {
+                        rot = 1;
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) {
+                            double2 x, y;
+                            x.x = c * p[j].x - s * q[j].x; x.y = c * p[j].y - s * q[j].y;
+                            y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
+                            cp[lane + 32 * j] = x;
+                            cq[lane + 32 * j] = y;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            // pairs across the blocks: A_w in registers, B columns through shared memory.  The squared norms of all
+            // columns are computed once per outer round and then UPDATED by the rotations (|p'|^2 = |p|^2 - t <p, q>,
+            // |q'|^2 = |q|^2 + t <p, q>, exact for the exact angle; at most RW updates apart, so they cannot drift):
+            // a round needs one dot product and one shuffle tree, not three.
+            double2 p[NQ];
+            double alpha;
+            {
+                const double2* ca = sm + (size_t)w * CH;
+                const double2* cbw = sm + (size_t)(RW + w) * CH;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    p[j] = ca[lane + 32 * j];
+                    const double2 qv = cbw[lane + 32 * j];
+                    a0 = fma(p[j].x, p[j].x, a0); a1 = fma(p[j].y, p[j].y, a1);
+                    b0 = fma(qv.x, qv.x, b0); b1 = fma(qv.y, qv.y, b1);
+                }
+                a0 += a1; b0 += b1;
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o2);
+                    b0 += __shfl_xor_sync(0xffffffffu, b0, o2);
+                }
+                alpha = a0;
+                if (lane == 0) s_bn[w] = b0;
+            }
+            __syncthreads();
+            for (int r = 0; r < ((dbg & 1) ? 0 : RW); ++r) {
+                const int jb = (w + r) & (RW - 1);
+                double2* cb = sm + (size_t)(RW + jb) * CH;
+                const double beta = s_bn[jb];
+                double2 q[NQ];
+                double g0 = 0.0, g1 = 0.0, g2a = 0.0, g3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NQ; j += 2) {
+                    q[j] = cb[lane + 32 * j];
+                    q[j + 1] = cb[lane + 32 * (j + 1)];
+                    g0 = fma(p[j].x, q[j].x, g0); g1 = fma(p[j].y, q[j].y, g1);
+                    g2a = fma(p[j + 1].x, q[j + 1].x, g2a); g3 = fma(p[j + 1].y, q[j + 1].y, g3);
+                }
+                double gamma = (g0 + g1) + (g2a + g3);
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
+                double c, s, tt;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, tt)) {
+                    rot = 1;
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) {
+                        double2 x, y;
+                        x.x = c * p[j].x - s * q[j].x; x.y = c * p[j].y - s * q[j].y;
+                        y.x = s * p[j].x + c * q[j].x; y.y = s * p[j].y + c * q[j].y;
+                        p[j] = x;
+                        cb[lane + 32 * j] = y;
+                    }
+                    alpha = fma(-tt, gamma, alpha);
+                    if (lane == 0) s_bn[jb] = fma(tt, gamma, beta);
+                }
+                __syncthreads();
+            }
+            // the blocks move on: A_w back to shared memory, then two bulk stores into the other half of the double
+            // buffer and one flag per block
+            {
+                double2* ca = sm + (size_t)w * CH;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) ca[lane + 32 * j] = p[j];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            ++g;
+            if (threadIdx.x == 0) {
+                double2* da = g2 + (g & 1u) * half_stride + dst_a;
+                double2* db = g2 + (g & 1u) * half_stride + dst_b;
+                bulk_s2g(da, sm, BLOCK_BYTES);
+                bulk_s2g(db, sm + (size_t)RW * CH, BLOCK_BYTES);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();                   // one fence, then both flags (fence + relaxed store = release)
+                st_relaxed(flag_a, g);
+                st_relaxed(flag_b, g);
+            }
+        }
+        if (aborted) break;
+        // did anybody rotate in this sweep?  one counting barrier per sweep
+        if (lane == 0) s_rot[w] = rot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int a = 0;
+            for (int i = 0; i < RW; ++i) a |= s_rot[i];
+            if (a) atomicOr(rotated + sweep, 1u);
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const bool ok = ring_wait(bar, (unsigned)C * (unsigned)(sweep + 1), abort_word);
+            s_ok = ok;
+            s_any = ok ? (int)ld_acquire(rotated + sweep) : 1;
+        }
+        __syncthreads();
+        if (!s_ok) { aborted = 1; break; }
+        if (dbg ? sweep == 5 : !s_any) { converged = 1; ++sweep; break; }
+    }
+    if (aborted) {
+        if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = -1; }
+        return;
+    }
+    // column norms -> eigenvalues, normalised columns into half 0 (slots in arbitrary order, sorted later).
+    // The last messages of the final round are still in flight to their receivers: wait for them like a round would.
+    if (threadIdx.x == 0) s_ok = ring_wait2(flagA + rank, flagB + rank, g, abort_word);
+    __syncthreads();
+    if (!s_ok) {
+        if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = -1; }
+        return;
+    }
+    for (int side = 0; side < 2; ++side) {
+        const size_t slot = (size_t)rank * 2 * RW + side * RW + w;
+        const double2* col = g2 + (g & 1u) * half_stride + slot * CH;
+        double2 v[NQ];
+        double nrm = 0.0;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) { v[j] = __ldcg(col + lane + 32 * j); nrm = fma(v[j].x, v[j].x, nrm); nrm = fma(v[j].y, v[j].y, nrm); }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o2);
+        nrm = sqrt(nrm);
+        const bool real_col = nrm > 0.0;
+        if (lane == 0) wtmp[slot] = real_col ? (factor_mode ? nrm * nrm : nrm - sigma) : (double)INFINITY;
+        const double inv = real_col ? 1.0 / nrm : 0.0;
+        double2* out = g2 + slot * CH;                            // half 0; same place when (g & 1) == 0
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) out[lane + 32 * j] = make_double2(v[j].x * inv, v[j].y * inv);
+    }
+    if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = converged; }
+}
+
+// gbuf half 0 (slots x len, padding slots / rows zeroed) <- columns of sym(G) + sigma I or rows of the factor U
+__global__ void jacobi_ring_init_kernel(const double* __restrict__ G, int64_t ldg, int n, int factor_mode,
+                                        const double* __restrict__ par, double* __restrict__ gbuf, int len, int slots,
+                                        unsigned* __restrict__ sync_words, int nsync) {
+    const double sigma = factor_mode ? 0.0 : par[0];
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = threadIdx.x; i < nsync; i += blockDim.x) sync_words[i] = 0u;
+    for (int c = blockIdx.y; c < slots; c += gridDim.y)
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < len; r += gridDim.x * blockDim.x) {
+            double v = 0.0;
+            if (r < n && c < n) v = factor_mode ? G[(int64_t)c * ldg + r]
+                                                : 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) + (r == c ? sigma : 0.0);
+            gbuf[(size_t)c * len + r] = v;
+        }
+}
+
 template <int NJ>
 static int launch_cluster(const double* G, int64_t ldg, int n, int W, int csize, int factor_mode, double tol, const double* par,
                           double* wtmp, double* qtmp, int* info, cudaStream_t st) {
@@ -475,6 +793,49 @@ static int launch_cluster(const double* G, int64_t ldg, int n, int W, int csize,
     return (int)cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<NJ>, G, ldg, n, W, factor_mode, tol, par, wtmp, qtmp, info);
 }
 
+template <int NQ>
+static int launch_ring(double* gbuf, int C, int factor_mode, double tol, const double* par, unsigned* sync_words,
+                       double* wtmp, int* info, cudaStream_t st) {
+    const size_t smem = (size_t)2 * RW * 64 * NQ * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(cudaFuncSetAttribute(jacobi_ring_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dbg = g_knob[KNOB_EIG_RING_DEBUG];
+    void* args[] = {&gbuf, &factor_mode, &tol, &par, &sync_words, &wtmp, &info, &dbg};
+    ++g_launches;
+    return (int)cudaLaunchCooperativeKernel((void*)jacobi_ring_kernel<NQ>, dim3((unsigned)C), dim3(RW * 32), args, smem, st);
+}
+
+static int syevj_ring(const double* g, int64_t ldg, int64_t n, int factor_mode, double tol, double* w, double* q,
+                      int64_t ldq, void* ws, int* info, cudaStream_t st) {
+    const int64_t len = n <= 512 ? 512 : 1024;          // the two instantiations of the kernel
+    const int C = (int)((n + 2 * RW - 1) / (2 * RW));
+    const int slots = 2 * RW * C;
+    if (C < 2 || C > sm_count()) return RL_E_ARG;
+    double* par = (double*)ws;
+    double* wtmp = par + 8;
+    double* gbuf = wtmp + (2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER);
+    unsigned* sync_words = (unsigned*)(gbuf + (size_t)2 * slots * len);
+    const int nsync = 2 * C + 2 + JC_MAX_SWEEPS;
+    int rc = 0;
+    if (!factor_mode) {
+        jacobi_shift_kernel<<<1, 1024, 0, st>>>(g, ldg, (int)n, par);
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    jacobi_ring_init_kernel<<<dim3((unsigned)((len + 127) / 128), (unsigned)slots), 128, 0, st>>>(
+        g, ldg, (int)n, factor_mode, par, gbuf, (int)len, slots, sync_words, nsync);
+    rc = check_launch();
+    if (rc) return rc;
+    if (len <= 512) rc = launch_ring<8>(gbuf, C, factor_mode, tol, par, sync_words, wtmp, info, st);
+    else rc = launch_ring<16>(gbuf, C, factor_mode, tol, par, sync_words, wtmp, info, st);
+    if (rc) return rc;
+    jacobi_sort_kernel<<<64, 1024, (size_t)slots * 12, st>>>(wtmp, gbuf, slots, (int)len, (int)n, 0.0, w, q, ldq);
+    return check_launch();
+}
+
 }  // namespace rl
 
 using namespace rl;
@@ -489,6 +850,8 @@ size_t rl_syevj_cluster_ws_bytes(int64_t n) {
     if (n <= 0) return 0;
     const int64_t len = (n + 63) / 64 * 64;
     const int64_t slots = 2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER;
+    if (n > rl_syevj_cluster_max_n())                  // ring kernel: double-buffered column store + sync words
+        return (size_t)(8 + slots + 2 * (n + 2 * RW) * (n <= 512 ? 512 : 1024)) * sizeof(double) + 4096;
     return (size_t)(8 + slots + slots * len) * sizeof(double) + 1024;
 }
 
@@ -556,7 +919,9 @@ int rl_syevj_cluster(const double* g, int64_t ldg, int64_t n, int factor_mode, d
     int* info_ws = (int*)(qtmp + (size_t)(2 * ((n + 1) / 2) + 2 * 32 * JC_MAX_CLUSTER) * len);
     int* info = info_d ? info_d : info_ws;
     Span span(PK_SYEVJ, st, 2.0 * n * n * 8, 0.0);
-    if (n > rl_syevj_cluster_max_n()) return syevj_grid(g, ldg, n, factor_mode, tol, w, q, ldq, ws, info, st);
+    if (n > rl_syevj_cluster_max_n())
+        return g_knob[KNOB_EIG_GRID_FLAT] ? syevj_grid(g, ldg, n, factor_mode, tol, w, q, ldq, ws, info, st)
+                                          : syevj_ring(g, ldg, n, factor_mode, tol, w, q, ldq, ws, info, st);
     // smallest cluster whose CTAs hold their pairs within 32 warps and the shared-memory budget
     // (<= 16 warps per CTA when possible: the FP64 pipe of one SM issues 2 warp-DFMAs per clock)
     int csize = 1, W = npairs;

@@ -175,6 +175,37 @@ def test_cluster_jacobi_eigh(rt, n, kind):
         assert abs(int(info[0]) - sweeps) <= 1, (info, sweeps)
 
 
+@pytest.mark.parametrize('n', [321, 336, 337, 512, 513, 777, 1000, 1024])
+@pytest.mark.parametrize('kind', ['random', 'neardiag', 'clustered'])
+def test_ring_jacobi_eigh(rt, n, kind):
+    """Orders beyond one cluster: the two-level ring tournament over the whole GPU (point-to-point block exchange
+    through L2); the flat one-barrier-per-round kernel stays behind a knob and must agree."""
+    rng = np.random.RandomState(n)
+    if kind == 'random':
+        G = rng.randn(n, n); G = G + G.T
+    elif kind == 'neardiag':
+        G = np.diag(np.sort(rng.rand(n)) * 100) + 1e-5 * rng.randn(n, n); G = 0.5 * (G + G.T)
+    else:
+        q, _ = np.linalg.qr(rng.randn(n, n))
+        G = (q * np.repeat(np.arange(1, n // 3 + 2), 3)[:n]) @ q.T
+    w, Q, info = _eig(rt, G)
+    wr = np.linalg.eigvalsh(G)
+    scale = max(1.0, np.max(np.abs(wr)))
+    assert info[1] == 1, info
+    assert np.max(np.abs(w - wr)) <= 1e-13 * scale * n
+    assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-13 * n
+    assert np.max(np.abs(G @ Q - Q * w[None, :])) <= 1e-13 * scale * n
+    assert np.all(np.diff(w) >= 0)
+    if n in (337, 1000) and kind == 'random':
+        rt.lib.rl_debug_set_knob(14, 1)
+        try:
+            w2, Q2, info2 = _eig(rt, G)
+        finally:
+            rt.lib.rl_debug_set_knob(14, 0)
+        assert info2[1] == 1
+        assert np.max(np.abs(w2 - w)) <= 1e-13 * scale * n
+
+
 @pytest.mark.parametrize('n', [1, 7, 64, 130, 321, 500, 1000])
 @pytest.mark.parametrize('cond', [1e2, 1e8])
 def test_potrf_and_jacobi_on_the_factor(rt, n, cond):

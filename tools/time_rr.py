@@ -133,8 +133,20 @@ def big(emit):
         def sym():
             check(lib.rl_small_eigh(G.data_ptr(), n, n, 0.0, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
         t_sym = timeit(sym, 3)
+        sw_sym = int(info[0])
+        lib.rl_debug_set_knob(14, 1)          # flat grid kernel (one grid barrier per round), for comparison
+        t_fac_flat = timeit(fac, 3)
+        sw_flat = int(info[0])
+        lib.rl_debug_set_knob(14, 0)
+        dbg = {}
+        for mode, name in ((1, 'ring6_exchange_only_ms'), (2, 'ring6_compute_only_ms'), (3, 'ring6_load_store_only_ms')):
+            lib.rl_debug_set_knob(15, mode)       # six sweeps with parts switched off (results meaningless)
+            dbg[name] = round(timeit(fac, 3), 3)
+        lib.rl_debug_set_knob(15, 0)
+        emit(order=n, **dbg)
         emit(order=n, potrf_ms=round(t_potrf, 3), eigh_factor_ms=round(t_fac, 3), eigh_factor_sweeps=sw_fac,
-             eigh_sym_ms=round(t_sym, 3), eigh_sym_sweeps=int(info[0]))
+             eigh_sym_ms=round(t_sym, 3), eigh_sym_sweeps=sw_sym, eigh_factor_flat_ms=round(t_fac_flat, 3),
+             eigh_factor_flat_sweeps=sw_flat)
 
 
 if __name__ == '__main__':
