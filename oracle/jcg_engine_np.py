@@ -133,9 +133,10 @@ def _rotate(B, p, q, tol2):
         return False
     delta = beta - alpha
     h = delta * delta + 4.0 * gamma * gamma
-    t = (2.0 if delta >= 0 else -2.0) * gamma / (abs(delta) + np.sqrt(h))
-    c = 1.0 / np.sqrt(1.0 + t * t)
-    s = c * t
+    r = 1.0 / np.sqrt(h)                       # cos 2theta = |delta| r, |theta| <= pi/4 (no division, no tangent:
+    c2 = 0.5 + 0.5 * abs(delta) * r            # the form csrc/jacobi.cu uses)
+    c = np.sqrt(c2)
+    s = (gamma if delta >= 0 else -gamma) * r / c
     B[:, p], B[:, q] = c * bp - s * bq, s * bp + c * bq
     return True
 

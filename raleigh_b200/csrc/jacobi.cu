@@ -57,19 +57,25 @@ jacobi_shift_kernel(const double* __restrict__ G, int64_t ld, int n, double* __r
     }
 }
 
-// Rotation of a column pair from its three dot products.  One rsqrt for sqrt(delta^2 + 4 gamma^2), one
-// division and one rsqrt for the cosine: the dependent chain of double-precision special functions is
-// what a round costs, so the textbook form (two divisions, two square roots, one reciprocal) is avoided.
+// Rotation of a column pair from its three dot products, |theta| <= pi/4.  Measured on B200
+// (tools/ubench/fp64_lat.cu): DFMA 8 cycles dependent, rsqrt 62, division 119 -- and since every lane of the
+// warp computes the same scalars, the chain also costs FP64 issue slots (2 cycles per warp instruction and
+// scheduler).  So: no division and no tangent.  With r = 1/sqrt(delta^2 + 4 gamma^2):
+//   cos 2theta = |delta| r,  c^2 = (1 + cos 2theta)/2,  c = c^2 rsqrt(c^2),  s = sign(delta) gamma r / c
+// (c^2 + s^2 = h r^2 = 1 to rounding, like any computed rotation): two rsqrt and ~10 DFMA, 165 cycles.
+// dn = change of |p|^2 = minus the change of |q|^2 under the rotation, for the callers that track norms.
 __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol2, double& c,
-                                                double& s, double& t) {
-    c = 1.0; s = 0.0; t = 0.0;
+                                                double& s, double& dn) {
+    c = 1.0; s = 0.0; dn = 0.0;
     if (!(gamma * gamma > tol2 * alpha * beta)) return false;      // also false for zero (padding) columns
     const double delta = beta - alpha;
     const double h = fma(delta, delta, 4.0 * gamma * gamma);
-    const double den = fabs(delta) + h * rsqrt(h);
-    t = (delta >= 0.0 ? 2.0 : -2.0) * gamma / den;
-    c = rsqrt(fma(t, t, 1.0));
-    s = c * t;
+    const double r = rsqrt(h);
+    const double c2 = fma(0.5 * fabs(delta), r, 0.5);
+    const double rc = rsqrt(c2);
+    c = c2 * rc;
+    s = (delta >= 0.0 ? gamma : -gamma) * r * rc;
+    dn = s * fma(s, delta, -2.0 * c * gamma);
     return true;
 }
 
@@ -94,6 +100,7 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
     constexpr int LEN = 64 * NJ;                                 // padded column length (doubles)
     double* buf = reinterpret_cast<double*>(jc_smem);            // [2][2W][LEN]: A block = columns 0..W-1, B block = W..2W-1
     __shared__ int s_rot[32];
+    __shared__ double s_bn[32];                                  // squared norms of the B columns
     __shared__ int s_flag[JC_MAX_SWEEPS][JC_MAX_CLUSTER];        // meaningful in CTA 0 only
     __shared__ int s_any;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -147,8 +154,12 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
     const int P = (W + 1) & ~1;                       // players of the intra-block tournament (one dummy if W is odd)
     const int nouter = C > 1 ? 2 * C - 1 : 1;
     int cur = 0, sweep = 0, converged = 0;
+    // cycle counts of CTA 0 by phase (intra-block rounds | norms | cross-block rounds | block exchange), read by
+    // tools/time_rr.py from the workspace: four clock reads per outer round
+    long long cyc_intra = 0, cyc_norms = 0, cyc_cross = 0, cyc_xchg = 0;
     for (; sweep < JC_MAX_SWEEPS; ++sweep) {
         int rot = 0;
+        long long tk = clock64();
         // (1) pairs inside each block
         for (int t = 0; t < P - 1; ++t) {
             for (int task = w; task < P; task += W) {
@@ -191,36 +202,50 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
             }
             __syncthreads();
         }
-        // (2) pairs across blocks: W local rounds per outer round, then the blocks move on
+        { const long long t1 = clock64(); cyc_intra += t1 - tk; tk = t1; }
+        // (2) pairs across blocks: W local rounds per outer round, then the blocks move on.  Squared norms are
+        // computed once per outer round and then updated by the rotations (at most W updates apart): a round needs
+        // ONE dot product and one shuffle tree -- with 16 warps the 64-bit shuffles of three trees alone cost
+        // 480 cycles per round (32 lanes per clock and SM), one tree 176.
         for (int o = 0; o < nouter; ++o) {
             double2* ca = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)w * LEN);
             double2 p[NJ];
             double alpha = 0.0;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                p[j] = ca[lane + 32 * j];
-                alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
-            }
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) alpha += __shfl_xor_sync(0xffffffffu, alpha, o2);
-            for (int r = 0; r < W; ++r) {
-                int jb = w + r; if (jb >= W) jb -= W;
-                double2* cb = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)(W + jb) * LEN);
-                double2 q[NJ];
-                double beta = 0.0, gamma = 0.0;
+            {
+                const double2* cbw = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(W + w) * LEN);
+                double b0 = 0.0;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    q[j] = cb[lane + 32 * j];
-                    beta = fma(q[j].x, q[j].x, beta); beta = fma(q[j].y, q[j].y, beta);
-                    gamma = fma(p[j].x, q[j].x, gamma); gamma = fma(p[j].y, q[j].y, gamma);
+                    p[j] = ca[lane + 32 * j];
+                    const double2 qv = cbw[lane + 32 * j];
+                    alpha = fma(p[j].x, p[j].x, alpha); alpha = fma(p[j].y, p[j].y, alpha);
+                    b0 = fma(qv.x, qv.x, b0); b0 = fma(qv.y, qv.y, b0);
                 }
 #pragma unroll
                 for (int o2 = 16; o2 > 0; o2 >>= 1) {
-                    beta += __shfl_xor_sync(0xffffffffu, beta, o2);
-                    gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, o2);
+                    b0 += __shfl_xor_sync(0xffffffffu, b0, o2);
                 }
-                double c, s, t;
-                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, t)) {
+                if (lane == 0) s_bn[w] = b0;
+            }
+            __syncthreads();
+            { const long long t1 = clock64(); cyc_norms += t1 - tk; tk = t1; }
+            for (int r = 0; r < W; ++r) {
+                int jb = w + r; if (jb >= W) jb -= W;
+                double2* cb = reinterpret_cast<double2*>(buf + cur * bufstride + (size_t)(W + jb) * LEN);
+                const double beta = s_bn[jb];
+                double2 q[NJ];
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    q[j] = cb[lane + 32 * j];
+                    g0 = fma(p[j].x, q[j].x, g0); g1 = fma(p[j].y, q[j].y, g1);
+                }
+                double gamma = g0 + g1;
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) gamma += __shfl_xor_sync(0xffffffffu, gamma, o2);
+                double c, s, dn;
+                if (jacobi_rotation(alpha, beta, gamma, tol2, c, s, dn)) {
                     rot = 1;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
@@ -230,12 +255,12 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
                         p[j] = x;
                         cb[lane + 32 * j] = y;
                     }
-                    // |p'|^2 = |p|^2 - t <p, q> exactly; recomputed from the column at the start of every outer
-                    // round (at most W updates apart), so the shortcut cannot drift
-                    alpha = fma(-t, gamma, alpha);
+                    alpha += dn;
+                    if (lane == 0) s_bn[jb] = beta - dn;
                 }
                 __syncthreads();
             }
+            { const long long t1 = clock64(); cyc_cross += t1 - tk; tk = t1; }
             if (C > 1) {
                 // A_w (registers) and B_w (shared memory) go to their next CTA, other buffer
                 const double2* cbw = reinterpret_cast<const double2*>(buf + cur * bufstride + (size_t)(W + w) * LEN);
@@ -253,6 +278,7 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
                 for (int j = 0; j < NJ; ++j) ca[lane + 32 * j] = p[j];
                 __syncthreads();
             }
+            { const long long t1 = clock64(); cyc_xchg += t1 - tk; tk = t1; }
         }
         // did anybody rotate in this sweep?
         if (lane == 0) s_rot[w] = rot;
@@ -302,7 +328,11 @@ jacobi_cluster_kernel(const double* __restrict__ G, int64_t ldg, int n, int W, i
             if (r0 + 1 < n) qtmp[(size_t)slot * LEN + r0 + 1] = v[j].y * inv;
         }
     }
-    if (rank == 0 && threadIdx.x == 0) { info[0] = sweep; info[1] = converged; }
+    if (rank == 0 && threadIdx.x == 0) {
+        info[0] = sweep; info[1] = converged;
+        long long* prof = reinterpret_cast<long long*>(const_cast<double*>(par) + 4);
+        prof[0] = cyc_intra; prof[1] = cyc_norms; prof[2] = cyc_cross; prof[3] = cyc_xchg;
+    }
 }
 
 // ascending order: w[rank] = value, Q[r][rank] = qtmp[slot][r]; every CTA ranks all slots, then scatters its share.
@@ -674,8 +704,8 @@ jacobi_ring_kernel(double* __restrict__ gbuf, int factor_mode, double tol, const
                         p[j] = x;
                         cb[lane + 32 * j] = y;
                     }
-                    alpha = fma(-tt, gamma, alpha);
-                    if (lane == 0) s_bn[jb] = fma(tt, gamma, beta);
+                    alpha += tt;
+                    if (lane == 0) s_bn[jb] = beta - tt;
                 }
                 __syncthreads();
             }

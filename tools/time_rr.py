@@ -93,6 +93,9 @@ def main():
                 check(lib.rl_small_eigh(G.data_ptr(), n, p, 0.0, w.data_ptr(), Q.data_ptr(), n, ews.data_ptr(), ewsb, info.data_ptr(), st()))
             res['eigh_%d_ms' % p] = round(timeit(eig, 10), 4)
             res['eigh_%d_sweeps' % p] = int(info[0])
+            if p <= 320:         # cycle counts of CTA 0 by phase (csrc/jacobi.cu writes them behind the parameters)
+                cyc = ews[4:8].view(torch.int64).cpu().numpy()
+                res['eigh_%d_kcycles_intra_norms_cross_exchange' % p] = [int(c // 1000) for c in cyc]
         B = up(rng.randn(n, n))
 
         def trsm():
