@@ -297,6 +297,58 @@ def hook_device_finalize_svd():
     cls._finalize_svd = staticmethod(_finalize)
 
 
+class _LraNumpyProxy:
+    """numpy for raleigh/interfaces/lra.py: `concatenate` of two device-data handles (see vectors.DeviceData)
+    along axis 1 happens on the device; every other call, and every other argument, goes to NumPy."""
+
+    def __init__(self, np):
+        self._np = np
+
+    def __getattr__(self, name):
+        return getattr(self._np, name)
+
+    def concatenate(self, arrays, axis=0, *args, **kwargs):
+        from .vectors import DeviceData
+        arrays = tuple(arrays)
+        if axis == 1 and len(arrays) == 2 and not args and not kwargs and all(isinstance(a, DeviceData) for a in arrays) \
+                and all(a._vec is not None for a in arrays):
+            return arrays[0].concatenate(arrays[1])
+        arrays = tuple(self._np.asarray(a) if isinstance(a, DeviceData) else a for a in arrays)
+        return self._np.concatenate(arrays, axis, *args, **kwargs)
+
+
+LAZY_UPDATE_BYTES = 16 << 20
+
+
+def hook_device_lra_update():
+    """LowerRankApproximation.update (lra.py:158-379) runs verbatim, but while it runs the two big `data()` calls
+    of its left-factor growth (lra.py:287-290) stay on the device: see vectors.DeviceData.  Off with the device
+    solver switch (use_device_solver(False)) so that parity runs can compare both routes."""
+    try:
+        import numpy
+        import raleigh.interfaces.lra as rlra
+    except ImportError:
+        return
+    cls = rlra.LowerRankApproximation
+    if getattr(cls, '_reference_update', None) is not None:
+        return
+    cls._reference_update = cls.update
+    if not isinstance(rlra.numpy, _LraNumpyProxy):
+        rlra.numpy = _LraNumpyProxy(rlra.numpy)
+
+    def update(self, matrix, *args, **kwargs):
+        from . import vectors
+        lazy = DEVICE_SOLVER and hasattr(matrix.as_vectors(), '_rl_device_block')
+        saved = vectors.LAZY_DATA_MIN_BYTES
+        vectors.LAZY_DATA_MIN_BYTES = LAZY_UPDATE_BYTES if lazy else None
+        try:
+            return cls._reference_update(self, matrix, *args, **kwargs)
+        finally:
+            vectors.LAZY_DATA_MIN_BYTES = saved
+
+    cls.update = update
+
+
 def install(reference_path=None, sparse=True, dense=True):
     """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.
     Raises ImportError if the reference package cannot be found."""
@@ -326,4 +378,5 @@ def install(reference_path=None, sparse=True, dense=True):
     shim_host_hotspots()
     hook_device_solver()
     hook_device_finalize_svd()
+    hook_device_lra_update()
     return raleigh

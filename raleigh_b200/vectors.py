@@ -35,6 +35,84 @@ def _np_type(t):
 
 TC_MIN_VECTORS = 8                # below this the FMA-pipe / GEMV kernels are used
 
+# lra.update (lra.py:287-290) grows the left factor by `data()` -> numpy.concatenate(axis=1) -> `new_vectors(ndarray)`:
+# the whole factor (1.2 GB at the end of config 5) crosses PCIe twice per chunk.  While compat's hooked update runs,
+# data() of a block at least this big returns a DeviceData handle instead of a host copy; compat's numpy proxy
+# concatenates two handles on the device and new_vectors() adopts the result.  Any other use of a handle turns it
+# into the host array it stands for (`__array__`), so the reference code stays correct whatever it does with it.
+LAZY_DATA_MIN_BYTES = None
+
+
+class DeviceData:
+    """Stand-in for the ndarray `Vectors.data()` would return: a private device copy of the selected block."""
+
+    def __init__(self, vec, owned=False):
+        if owned:
+            self._vec = vec
+        else:
+            m = vec.nvec()
+            self._vec = Vectors._local(vec._n, m, vec._dtype)
+            vec.copy(self._vec)
+        self._host = None
+
+    # -- what the concatenation hook uses
+    def concatenate(self, other):
+        out = Vectors._local(self._vec._n, self._vec.nvec(), self._vec._dtype)
+        self._vec.copy(out)
+        out.append(other._vec, axis=1)
+        return DeviceData(out, owned=True)
+
+    def take(self):
+        """The block as Vectors (new_vectors(ndarray) semantics: a fresh container)."""
+        v, self._vec = self._vec, None
+        if v is None:
+            return Vectors(self._host)
+        return v
+
+    # -- ndarray behaviour on demand
+    def _array(self):
+        if self._host is None:
+            saved = LAZY_DATA_MIN_BYTES
+            globals()['LAZY_DATA_MIN_BYTES'] = None
+            try:
+                self._host = self._vec.data()
+            finally:
+                globals()['LAZY_DATA_MIN_BYTES'] = saved
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._array()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getattr__(self, name):
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return getattr(self._array(), name)
+
+    def __getitem__(self, key):
+        return self._array()[key]
+
+    def __setitem__(self, key, value):
+        self._array()[key] = value
+
+    def __len__(self):
+        return len(self._array())
+
+    def __iter__(self):
+        return iter(self._array())
+
+
+def _device_data_binop(name):
+    def op(self, *args):
+        return getattr(self._array(), name)(*args)
+    op.__name__ = name
+    return op
+
+
+for _n in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__truediv__', '__rtruediv__', '__neg__',
+           '__abs__', '__matmul__', '__rmatmul__', '__pow__', '__lt__', '__le__', '__gt__', '__ge__', '__eq__', '__ne__'):
+    setattr(DeviceData, _n, _device_data_binop(_n))
+
 
 def block_gemm(code, a_ptr, lda, M, N, x_ptr, ldx, y_ptr, ldy, k, transp, alpha=1.0, beta=0.0):
     """Y = alpha X A^T (transp = 0) or alpha X A (transp = 1) + beta Y with A an (M, N) row-major block:
@@ -62,6 +140,8 @@ class Vectors:
     def __init__(self, arg, nvec=0, data_type=None, shallow=False):
         self._buf = None
         self._off = 0                       # first vector of this object inside the buffer
+        if isinstance(arg, DeviceData):
+            arg = numpy.asarray(arg)
         if isinstance(arg, Vectors):
             first, nv = arg.selected()
             self._set_type(arg.data_type())
@@ -201,6 +281,8 @@ class Vectors:
     def new_vectors(self, arg=0, dim=None):
         if isinstance(arg, numbers.Number):
             return Vectors(self.dimension() if dim is None else dim, int(arg), self.data_type())
+        if isinstance(arg, DeviceData):
+            return arg.take()
         return Vectors(arg)
 
     @staticmethod
@@ -282,7 +364,8 @@ class Vectors:
             st = dev.stream()
             check(lib.rl_copy(self._code, buf.ptr, ld_new, self._ptr(0), self._ld, m, n, st))
             check(lib.rl_copy(self._code, buf.ptr + n * self._w, ld_new, other._ptr(0), other._ld, m, n_other, st))
-            self._buf, self._off, self._ld, self._n, self._cap = buf, 0, ld_new, n_new, m
+            self._buf, self._off, self._ld, self._n, self._ng, self._cap = buf, 0, ld_new, n_new, n_new, m
+            self._touch()
             return
         i, m = self.selected()
         j, l = other.selected()
@@ -512,6 +595,8 @@ class Vectors:
         m = self.nvec()
         if m < 1:
             return numpy.ndarray((m, self._ng), dtype=self._dtype)
+        if LAZY_DATA_MIN_BYTES is not None and self._shard is None and m * self._n * self._w >= LAZY_DATA_MIN_BYTES:
+            return DeviceData(self)                    # inside compat's hooked lra.update only
         local = dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
         if self._shard is None:
             return local
@@ -566,6 +651,8 @@ class Matrix:
 
     def __init__(self, arg):
         self._mshard = None                # (ctx, row0) when this process holds a row slab
+        if isinstance(arg, DeviceData):
+            arg = numpy.asarray(arg)
         if isinstance(arg, Vectors):
             f, m = arg.selected()
             if arg.is_sharded():

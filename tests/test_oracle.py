@@ -128,6 +128,8 @@ def _run_backend_case(Vectors, Matrix, g, close):
     X = Vectors(u.copy())
     X.append(Vectors(v.copy()), axis=1)
     close(X.data(), g['append1'], dt)
+    assert X.dimension() == g['append1'].shape[1] and X.new_vectors(2).dimension() == X.dimension()
+    close(X.dots(X), np.sum(g['append1'].astype(np.float64) ** 2, axis=1), dt)
     X = Vectors(u.copy())
     Z = X.reference()
     Z.select(nv // 2, nv // 2)

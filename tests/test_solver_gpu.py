@@ -113,6 +113,45 @@ def test_pca_small(gpu_backend, ref):
     assert ef <= 0.1 + 1e-3
 
 
+def test_incremental_pca_left_factor_stays_on_the_device(gpu_backend, ref):
+    """lra.update (lra.py:287-290) grows the left factor through data() -> numpy.concatenate -> new_vectors();
+    compat keeps those blocks on the device (vectors.DeviceData).  Same result as the host round trip, bit for bit;
+    with the threshold at zero every data() inside update() goes through the stand-in, which then has to behave
+    like the ndarray it replaces."""
+    from raleigh.interfaces.pca import pca, pca_error
+    from raleigh.examples.pca.generate_matrix import generate
+    from raleigh_b200 import compat, vectors
+    np.random.seed(1)
+    A, sigma, u, v = generate(900, 400, 200, pca=True)
+    results = []
+    taken = []
+    orig_take = vectors.DeviceData.take
+
+    def counting_take(self):
+        taken.append(1)
+        return orig_take(self)
+
+    vectors.DeviceData.take = counting_take
+    saved = compat.LAZY_UPDATE_BYTES
+    try:
+        for threshold in (1 << 60, 0, 64 << 10):
+            compat.LAZY_UPDATE_BYTES = threshold
+            del taken[:]
+            np.random.seed(7)
+            mean, trans, comps = pca(A, batch_size=300, tol=0.1, arch='gpu!', opt=ref.Options())
+            results.append((mean, trans, comps, len(taken)))
+    finally:
+        compat.LAZY_UPDATE_BYTES = saved
+        vectors.DeviceData.take = orig_take
+    assert results[0][3] == 0 and results[1][3] >= 2 and results[2][3] >= 2     # two updates, one adoption each
+    for mean, trans, comps, _ in results[1:]:
+        assert np.array_equal(mean, results[0][0])
+        assert np.array_equal(trans, results[0][1])
+        assert np.array_equal(comps, results[0][2])
+    em, ef = pca_error(A, *results[1][:3])
+    assert ef <= 0.1 + 1e-3
+
+
 def test_pca_doctest(gpu_backend, ref):
     """interfaces/pca.py:92-133 known answers, arch='gpu!'."""
     g = np.load(os.path.join(GOLDEN, 'pca.npz'))
