@@ -115,8 +115,20 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int jw = warp % JS, rw = warp / JS;
     const int g = lane >> 2, c = lane & 3;
-    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ * JS) + jw * (8 * NJ);
-    const int chunk = blockIdx.x;
+    // multi-tile products: one-dimensional grid with the TILES of a row chunk adjacent in launch order, so that the
+    // CTAs that read the same rows of S and O run at the same time and share them through L2 (chunk-major order
+    // streams every vector from HBM once per tile that uses it: 4.3x the algorithmic traffic at m = k = 120)
+    int bz = blockIdx.z, by = blockIdx.y, bx = blockIdx.x, nchunks = gridDim.x;
+    if (gridDim.y == 1 && gridDim.z == 1) {
+        const int tj = (m + 8 * NJ * JS - 1) / (8 * NJ * JS), ti = (k + 8 * NI - 1) / (8 * NI);
+        const int t = bx % (tj * ti);
+        bx /= tj * ti;
+        nchunks /= tj * ti;
+        by = t % tj;
+        bz = t / tj;
+    }
+    const int i0 = bz * (8 * NI), j0 = by * (8 * NJ * JS) + jw * (8 * NJ);
+    const int chunk = bx;
 
     const double* po[NI];
     const double* ps[NJ];
@@ -134,7 +146,7 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
 
     const int64_t c_begin = interleave ? (int64_t)chunk * (16 * RW) : (int64_t)chunk * rows_per_cta;
     const int64_t c_end = interleave ? n : (c_begin + rows_per_cta < n ? c_begin + rows_per_cta : n);
-    const int64_t r_step = interleave ? (int64_t)gridDim.x * (16 * RW) : (int64_t)(16 * RW);
+    const int64_t r_step = interleave ? (int64_t)nchunks * (16 * RW) : (int64_t)(16 * RW);
     int64_t r = c_begin + rw * 16;
     // SAME: X.dot(X) with a single tile -- both operands are the same fragments, load once
     if (fast) {
@@ -195,7 +207,7 @@ gram_dmma_kernel(const double* __restrict__ S, int64_t lds, int m, const double*
         }
     __syncthreads();
     double* out = part + (int64_t)chunk * k * m;
-    const int jbase = blockIdx.y * (8 * NJ * JS);
+    const int jbase = by * (8 * NJ * JS);
     for (int e = threadIdx.x; e < TILE; e += DW * 32) {
         double v = red[0][e];
 #pragma unroll
@@ -321,6 +333,8 @@ template <int NI>
 static int launch_dmma_nj(const GramPlan& p, const double* S, int64_t lds, int m, const double* O, int64_t ldo,
                           int k, int64_t n, int fast, double* part, cudaStream_t st) {
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
+    if (p.tiles_i * p.tiles_j > 1 && !g_knob[KNOB_GRAM_CHUNK_MAJOR])
+        grid = dim3((unsigned)(p.chunks * p.tiles_j * p.tiles_i), 1, 1);
     const bool same = S == O && lds == ldo && m == k && p.tiles_i == 1 && p.tiles_j == 1 && p.ni == p.nj && p.js == 1;
 #define RL_GRAM_LAUNCH(NJ_, JS_, SAME_) \
     gram_dmma_kernel<NI, NJ_, JS_, SAME_><<<grid, GRAM_THREADS, (GRAM_WARPS / JS_) * JS_ * NI * NJ_ * 64 * sizeof(double), st>>>(S, lds, m, O, ldo, k, n, p.rows_per_cta, fast, part, g_gram_prefetch | ((g_knob[KNOB_GRAM_INTERLEAVE] & 1) << 8))
