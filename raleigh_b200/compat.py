@@ -338,9 +338,14 @@ def hook_device_lra_update():
 
     def update(self, matrix, *args, **kwargs):
         from . import vectors
-        lazy = DEVICE_SOLVER and hasattr(matrix.as_vectors(), '_rl_device_block')
+        from . import dist
+        ctx = dist.current()
+        sharded = ctx is not None and ctx.world > 1
+        lazy = (DEVICE_SOLVER or sharded) and hasattr(matrix.as_vectors(), '_rl_device_block')
         saved = vectors.LAZY_DATA_MIN_BYTES
-        vectors.LAZY_DATA_MIN_BYTES = LAZY_UPDATE_BYTES if lazy else None
+        # sample-partitioned run: the left factor is row-sharded and its pieces must be joined process by process
+        # (Vectors.append(axis=1)), which only the device route does -- every data() goes through the stand-in
+        vectors.LAZY_DATA_MIN_BYTES = (0 if sharded else LAZY_UPDATE_BYTES) if lazy else None
         try:
             return cls._reference_update(self, matrix, *args, **kwargs)
         finally:

@@ -41,24 +41,19 @@ TC_MIN_VECTORS = 8                # below this the FMA-pipe / GEMV kernels are u
 # concatenates two handles on the device and new_vectors() adopts the result.  Any other use of a handle turns it
 # into the host array it stands for (`__array__`), so the reference code stays correct whatever it does with it.
 LAZY_DATA_MIN_BYTES = None
+_SAMPLE_LOCAL = [False]            # True while SampleVectors builds its local block from the matrix
 
 
 class DeviceData:
     """Stand-in for the ndarray `Vectors.data()` would return: a private device copy of the selected block."""
 
     def __init__(self, vec, owned=False):
-        if owned:
-            self._vec = vec
-        else:
-            m = vec.nvec()
-            self._vec = Vectors._local(vec._n, m, vec._dtype)
-            vec.copy(self._vec)
+        self._vec = vec if owned else Vectors(vec)        # private copy of the selected block (keeps the sharding)
         self._host = None
 
     # -- what the concatenation hook uses
     def concatenate(self, other):
-        out = Vectors._local(self._vec._n, self._vec.nvec(), self._vec._dtype)
-        self._vec.copy(out)
+        out = Vectors(self._vec)
         out.append(other._vec, axis=1)
         return DeviceData(out, owned=True)
 
@@ -137,6 +132,11 @@ class Vectors:
     MAX_INC = 1024
 
     # ------------------------------------------------------------------ ctor
+    def __new__(cls, arg=None, nvec=0, data_type=None, shallow=False):
+        if cls is Vectors and isinstance(arg, Matrix) and arg._mshard is not None and not _SAMPLE_LOCAL[0]:
+            return SampleVectors(arg, shallow)      # not a Vectors instance: __init__ below is not run on it
+        return object.__new__(cls)
+
     def __init__(self, arg, nvec=0, data_type=None, shallow=False):
         self._buf = None
         self._off = 0                       # first vector of this object inside the buffer
@@ -349,10 +349,10 @@ class Vectors:
         if other.nvec() < 1:
             return
         if axis == 1:
-            if self._shard is not None or other._shard is not None:
-                raise NotImplementedError('append(axis=1) of row-sharded vectors')
-            m, n = self.shape()
-            l, n_other = other.shape()
+            if (self._shard is None) != (other._shard is None):
+                raise ValueError('append(axis=1) of a row-sharded and a replicated block')
+            m, n = self.nvec(), self._n
+            l, n_other = other.nvec(), other._n
             if m != l:
                 raise ValueError('Cannot append %d vectors to %d vectors' % (l, m))
             if self.data_type() != other.data_type():
@@ -362,9 +362,21 @@ class Vectors:
             ld_new = dev.padded_ld(n_new, self._w)
             buf = dev.Buffer(m * ld_new * self._w)
             st = dev.stream()
-            check(lib.rl_copy(self._code, buf.ptr, ld_new, self._ptr(0), self._ld, m, n, st))
-            check(lib.rl_copy(self._code, buf.ptr + n * self._w, ld_new, other._ptr(0), other._ld, m, n_other, st))
-            self._buf, self._off, self._ld, self._n, self._ng, self._cap = buf, 0, ld_new, n_new, n_new, m
+            check(lib.rl_copy(self._code, buf.ptr, ld_new, self._ptr(self._sel[0]), self._ld, m, n, st))
+            check(lib.rl_copy(self._code, buf.ptr + n * self._w, ld_new, other._ptr(other._sel[0]), other._ld, m,
+                              n_other, st))
+            ng_new = n_new
+            if self._shard is not None:
+                # every process appends ITS rows: the logical row order of the result is process-major
+                # (rows of process 0 of both blocks, then process 1, ...), a contiguous partition again
+                ctx = self._shard[0]
+                ng_new = self._ng + other._ng
+                row0 = self._shard[1] + other._shard[1]
+                ctx.register(ng_new, row0, n_new)
+                self._shard = (ctx, row0)
+            self._buf, self._off, self._ld, self._n, self._ng, self._cap = buf, 0, ld_new, n_new, ng_new, m
+            self._nvec = m
+            self._sel = (0, m)
             self._touch()
             return
         i, m = self.selected()
@@ -595,7 +607,7 @@ class Vectors:
         m = self.nvec()
         if m < 1:
             return numpy.ndarray((m, self._ng), dtype=self._dtype)
-        if LAZY_DATA_MIN_BYTES is not None and self._shard is None and m * self._n * self._w >= LAZY_DATA_MIN_BYTES:
+        if LAZY_DATA_MIN_BYTES is not None and m * self._n * self._w >= LAZY_DATA_MIN_BYTES:
             return DeviceData(self)                    # inside compat's hooked lra.update only
         local = dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
         if self._shard is None:
@@ -644,6 +656,120 @@ class Vectors:
         See svd.py for the on-device algorithm."""
         from .svd import block_svd
         return block_svd(self)
+
+
+class SampleVectors:
+    """The rows of a SAMPLE-PARTITIONED data matrix viewed as vectors (AMatrix.as_vectors(), dense_matrix.py:40-43,
+    used by lra.update, lra.py:182-260): every process holds all components of SOME of the vectors.  The object
+    answers for the whole set -- nvec() is the global count, per-vector results are concatenated over the
+    processes (process-major order, the order of the logical matrix), sums over the vectors are all-reduced --
+    so that the reference's update code, which runs replicated on every process, sees one consistent matrix.
+    Only what that code uses is provided; selections are not."""
+    _rl_device_block = True
+
+    def __init__(self, matrix, shallow=True):
+        ctx, row0 = matrix._mshard
+        _SAMPLE_LOCAL[0] = True
+        try:
+            self._loc = Vectors(matrix, shallow=shallow)         # this process's rows, an ordinary local block
+        finally:
+            _SAMPLE_LOCAL[0] = False
+        self._ctx, self._row0 = ctx, int(row0)
+        self._counts = ctx.allgather_counts(self._loc.nvec())
+        self._nvg = int(sum(self._counts))
+        assert self._row0 == sum(self._counts[:ctx.rank])
+
+    # -- bookkeeping
+    def nvec(self):
+        return self._nvg
+
+    def dimension(self):
+        return self._loc.dimension()
+
+    def data_type(self):
+        return self._loc.data_type()
+
+    def is_complex(self):
+        return False
+
+    def selected(self):
+        return (0, self._nvg)
+
+    def select(self, nv, first=0):
+        if first != 0 or nv != self._nvg:
+            raise NotImplementedError('selection of sample-partitioned vectors')
+
+    def select_all(self):
+        pass
+
+    def is_sharded(self):
+        return False
+
+    def local(self):
+        return self._loc
+
+    def new_vectors(self, arg=0, dim=None):
+        return self._loc.new_vectors(arg, dim)
+
+    def _rows(self, a, axis):
+        """This process's part of a host array indexed by the (global) vectors along `axis`."""
+        a = numpy.asarray(a)
+        n = self._loc.nvec()
+        if a.shape[axis] == self._nvg:
+            return a[self._row0:self._row0 + n] if axis == 0 else a[:, self._row0:self._row0 + n]
+        if a.shape[axis] == n:
+            return a
+        raise ValueError('array extent %d matches neither the global (%d) nor the local (%d) number of vectors'
+                         % (a.shape[axis], self._nvg, n))
+
+    # -- algebra
+    def dots(self, other, transp=False):
+        if transp:
+            w = self._loc.dots(other.local() if isinstance(other, SampleVectors) else other, transp=True)
+            return self._ctx.allreduce_host(w)
+        o = other.local() if isinstance(other, SampleVectors) else other
+        w = self._loc.dots(o)
+        return self._ctx.allgather_columns(w[None, :], self._counts)[0]
+
+    def multiply(self, q, output):
+        """output = q^T self with q (nvec, k): the sum runs over the vectors, i.e. over the processes."""
+        q = numpy.asarray(q)
+        if q.ndim == 1:
+            q = q.reshape(-1, 1)
+        self._loc.multiply(numpy.ascontiguousarray(self._rows(q, 0)), output)
+        _allreduce_block(self._ctx, output)
+
+    def add(self, other, s, q=None):
+        """self += s q^T other, q (other.nvec, nvec): row-local once q is cut to this process's vectors."""
+        if q is None:
+            o = other.local() if isinstance(other, SampleVectors) else other
+            return self._loc.add(o, s)
+        self._loc.add(other, s, numpy.ascontiguousarray(self._rows(q, 1)))
+
+    def scale(self, s, multiply=False):
+        self._loc.scale(numpy.ascontiguousarray(self._rows(numpy.asarray(s).reshape(-1), 0)), multiply)
+
+    def orthogonalize(self, other):
+        """q = <other, self>, self -= q^T other; q comes back as k vectors whose dimension is the (global) number of
+        vectors of self -- a row-sharded block like every other block over the samples."""
+        q = self._loc.orthogonalize(other)
+        q._ng = self._nvg
+        q._shard = (self._ctx, self._row0)
+        return q
+
+    def data(self):
+        local = self._loc.data()
+        return numpy.ascontiguousarray(self._ctx.allgather_columns(numpy.ascontiguousarray(local.T), self._counts).T)
+
+
+def _allreduce_block(ctx, v):
+    """Sum the selected (replicated-dimension) block of `v` over the processes, in place."""
+    import torch
+    m = v.nvec()
+    if m < 1 or ctx.world == 1:
+        return
+    host = v.data()
+    v.fill(ctx.allreduce_host(host))
 
 
 class Matrix:
@@ -771,12 +897,8 @@ class Matrix:
 
     def dots(self):
         """Squared 2-norms of the rows, one per row of the LOGICAL matrix (dense_numpy.py:177-179)."""
-        v = Vectors(self, shallow=True)
-        w = v.dots(v)
-        if self._mshard is not None:        # this process holds a row slab: concatenate the slabs' results
-            ctx = self._mshard[0]
-            w = ctx.allgather_columns(w.reshape(1, -1), ctx.allgather_counts(w.shape[0])).reshape(-1)
-        return w
+        v = Vectors(self, shallow=True)     # row slab of a sharded matrix: SampleVectors, results concatenated
+        return v.dots(v)
 
     def new_vectors(self, dim=None, nv=0):
         if dim is None:

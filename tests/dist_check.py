@@ -117,6 +117,31 @@ def main():
             print('sharded sparse eigen-solve ok: %d iterations, eigenvalue error %.1e, halo traffic %.2f MB'
                   % (solver.iteration, err, op.halo_bytes / 1e6))
 
+    # sample-partitioned rows as vectors (AMatrix.as_vectors on a sharded matrix): what lra.update uses
+    V = rb.Vectors(A, shallow=True)
+    assert type(V).__name__ == 'SampleVectors' and V.nvec() == M and V.dimension() == N
+    assert np.allclose(V.dots(V), np.sum(a.astype(np.float64) ** 2, axis=1), rtol=1e-4), 'sample dots'
+    e = np.ones((M, 1), dtype=np.float32)
+    s1 = V.new_vectors(1, N)
+    V.multiply(e, s1)
+    assert np.allclose(s1.data(), a.sum(axis=0, keepdims=True), rtol=1e-3, atol=1e-2), 'sample multiply (all-reduce)'
+    qmat, _ = np.linalg.qr(rng.randn(N, 5).astype(np.float32))
+    R0 = rb.Vectors(np.ascontiguousarray(qmat.T))
+    a2 = a.copy()
+    A2 = rb.Matrix(np.ascontiguousarray(a2[row0:row0 + mloc]))
+    V2 = rb.Vectors(A2, shallow=True)
+    L1 = V2.orthogonalize(R0)
+    assert L1.is_sharded() and L1.dimension() == M and L1.nvec() == 5
+    q_ref = a2 @ qmat                                   # (M, 5)
+    assert np.allclose(L1.data(), q_ref.T, rtol=1e-3, atol=1e-3), 'sample orthogonalize coefficients'
+    assert np.allclose(V2.data(), a2 - q_ref @ qmat.T, rtol=1e-3, atol=1e-3), 'sample orthogonalize residual'
+    # append(axis=1) of row-sharded blocks: process-major logical order
+    L2 = rb.Vectors(L1)
+    L2.append(L1, axis=1)
+    assert L2.is_sharded() and L2.dimension() == 2 * M and L2.local_dimension() == 2 * mloc
+    d2 = L2.dots(L2)
+    assert np.allclose(d2, 2 * np.sum(q_ref.astype(np.float64) ** 2, axis=0), rtol=1e-4), 'sharded append(axis=1)'
+
     # end to end: the reference's pca on the row-sharded matrix vs the golden CPU run
     if rb.find_reference() is not None:
         rb.install()
@@ -146,6 +171,21 @@ def main():
             print('sharded pca ok: components %d, pca_error %.3e %.3e, leading singular values within %.1e of exact (reference CPU run: %.1e), '
                   'all-reduces %d (%.1f MB)' % (comps.shape[0], em, ef, dev_sv, dev_gold, ctx.allreduce_calls,
                                                 ctx.allreduce_bytes / 1e6))
+        # BASELINE config 5 in miniature: incremental PCA with every chunk split over the processes
+        # (lra.icompute / lra.update verbatim on SampleVectors + row-sharded factors)
+        np.random.seed(1)
+        Ainc, sig, u, v = generate(400 * world * 3, 300, 150, pca=True)
+        per = Ainc.shape[0] // world
+        mine = np.ascontiguousarray(Ainc[rank * per:(rank + 1) * per])
+        np.random.seed(5)
+        mean, trans, comps = pca(mine, tol=0.1, batch_size=400, arch='gpu!', opt=Options())
+        assert trans.shape == (Ainc.shape[0], comps.shape[0]), trans.shape
+        em, ef = pca_error(Ainc, mean, trans, comps)       # rows of `trans` in process-major order = rows of Ainc
+        assert ef <= 0.1 + 2e-3, ef
+        assert np.max(np.abs(mean.reshape(-1) - Ainc.mean(axis=0))) < 1e-4
+        if rank == 0:
+            print('sharded incremental pca ok: %d chunks of %d rows over %d processes, components %d, pca_error %.3e %.3e'
+                  % (3, 400 * world, world, comps.shape[0], em, ef))
     tdist.barrier()
     if rank == 0:
         print('DIST_CHECK_OK world=%d' % world)
