@@ -25,14 +25,28 @@ ap.add_argument('--tol', type=float, default=0.05)
 ap.add_argument('--cpu', action='store_true')
 args = ap.parse_args()
 
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank = int(os.environ.get('RANK', '0'))
+if world > 1:
+    # sample-partitioned run (torchrun, one process per GPU): every process generates and keeps rows/world rows of
+    # the matrix -- the same right factor everywhere, its own left factor -- and feeds its share of every chunk
+    import torch.distributed as tdist
+    from raleigh_b200 import dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
+    tdist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', rank))))
+    dist.enable()
+    assert args.rows % world == 0 and args.chunk % world == 0
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 r = args.rank
 sigma = torch.arange(1, r + 1, device='cuda', dtype=torch.float32) ** (-0.75)
 v, _ = torch.linalg.qr(torch.randn(args.cols, r, generator=g, device='cuda'))
-u = torch.randn(args.rows, r, generator=g, device='cuda') / args.rows ** 0.5
+g.manual_seed(100 + rank)
+rows_here = args.rows // world
+u = torch.randn(rows_here, r, generator=g, device='cuda') / args.rows ** 0.5
 a = (u * sigma[None, :]) @ v.T
-a += 1e-3 * sigma[-1] * torch.randn(args.rows, args.cols, generator=g, device='cuda') / args.cols ** 0.5
+a += 1e-3 * sigma[-1] * torch.randn(rows_here, args.cols, generator=g, device='cuda') / args.cols ** 0.5
 A = a.cpu().numpy()
+args.chunk //= world
 with threadpool_limits(limits=1):
     np.random.seed(1)
     profile.reset(); profile.enable(True)
@@ -41,10 +55,14 @@ with threadpool_limits(limits=1):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     profile.enable(False)
 prof = profile.report()
-t = torch.as_tensor(trans, device='cuda'); c = torch.as_tensor(comps, device='cuda')
+t = torch.as_tensor(trans[rank * rows_here:(rank + 1) * rows_here], device='cuda'); c = torch.as_tensor(comps, device='cuda')
 ds = a - torch.as_tensor(mean, device='cuda').reshape(1, -1)
-ef = (torch.linalg.norm(t @ c - ds) / torch.linalg.norm(ds)).item()
-line = {'config': 'C5 (single GPU): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (args.rows, args.cols, args.chunk, args.tol),
+num, den = torch.linalg.norm(t @ c - ds) ** 2, torch.linalg.norm(ds) ** 2
+if world > 1:
+    both = torch.stack((num, den)); tdist.all_reduce(both); num, den = both[0], both[1]
+    tmax = torch.tensor([dt], device='cuda'); tdist.all_reduce(tmax, op=tdist.ReduceOp.MAX); dt = float(tmax.item())
+ef = float(torch.sqrt(num / den).item())
+line = {'config': 'C5 (%d GPU%s, samples partitioned): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (world, '' if world == 1 else 's', args.rows, args.cols, args.chunk * world, args.tol),
         'gpu_s': round(dt, 3), 'components': int(comps.shape[0]), 'pca_error_frobenius': ef,
         'device_ms': round(sum(v_['ms'] for v_ in prof.values()), 1),
         'kernels': {k: {'count': v_['count'], 'ms': round(v_['ms'], 1)} for k, v_ in prof.items()}}
@@ -54,4 +72,8 @@ if args.cpu:
     mean2, trans2, comps2 = pca(A, tol=args.tol, batch_size=args.chunk, arch='cpu', opt=Options())
     line['cpu_s'] = round(time.perf_counter() - t0, 2)
     line['cpu_components'] = int(comps2.shape[0])
-print(json.dumps(line), flush=True)
+if rank == 0:
+    print(json.dumps(line), flush=True)
+if world > 1:
+    tdist.barrier()
+    tdist.destroy_process_group()
