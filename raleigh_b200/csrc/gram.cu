@@ -427,9 +427,14 @@ static int gram_impl(int dtype, const void* s, int64_t lds, int64_t m, const voi
         // TMA-fed ring variant (gram_tma.cu): KNOB_GRAM_TMA 0 = default policy, -1 = off, 1/2 = forced mode
         const int tma_knob = g_knob[KNOB_GRAM_TMA];
         const int tma_mode = tma_knob > 0 ? tma_knob : (tma_knob == 0 ? RL_GRAM_TMA_DEFAULT : 0);
-        // multi-tile products (m or k > 32) are DMMA-bound either way: the register kernel stays
-        if (tma_mode > 0 && (tma_knob > 0 || (m <= 32 && k <= 32)) && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
-            rc = gram_tma((const double*)s, lds, m, (const double*)o, ldo, k, n, (double*)ws, &chunks, tma_mode, st);
+        // multi-tile products (m or k > 32) are DMMA-bound; from 64 vectors on the deep TMA ring (mode 1) feeds the
+        // tensor pipe better than register fragments do (r2z, tools/time_gram120.py: 120 x 120 17.1 -> 20.1 TFLOP/s,
+        // 96: 18.5 -> 22.1, 64: 18.2 -> 21.7; 48: no difference)
+        const bool multi = m > 32 || k > 32;
+        const bool multi_tma = multi && tma_knob == 0 && (m >= 64 || k >= 64) && m > 16 && k > 16;
+        if (tma_mode > 0 && (tma_knob > 0 || !multi || multi_tma) && gram_tma_ok(s, lds, m, o, ldo, k, n)) {
+            rc = gram_tma((const double*)s, lds, m, (const double*)o, ldo, k, n, (double*)ws, &chunks,
+                          multi_tma ? 1 : tma_mode, st);
             if (rc) return rc;
             gram_reduce_kernel<double, double><<<gram_reduce_blocks(km), 1024, 0, st>>>((const double*)ws, km, chunks, (double*)g);
             return check_launch();

@@ -45,12 +45,22 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
     uint64_t* empty = full + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.z * (8 * NI), j0 = blockIdx.y * (8 * NJ);
+    // multi-tile products come as a one-dimensional grid, the tiles of a row chunk adjacent (see gram.cu)
+    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, nchunks = gridDim.x;
+    if (gridDim.y == 1 && gridDim.z == 1) {
+        const int tj = (m + 8 * NJ - 1) / (8 * NJ), ti = (k + 8 * NI - 1) / (8 * NI);
+        const int t = bx % (tj * ti);
+        bx /= tj * ti;
+        nchunks /= tj * ti;
+        by = t % tj;
+        bz = t / tj;
+    }
+    const int i0 = bz * (8 * NI), j0 = by * (8 * NJ);
     // contiguous: CTA c owns rows [c * rows_per_cta, (c+1) * rows_per_cta); interleaved: CTA c owns
     // stages c, c + grid, c + 2 grid, ... so that the CTAs running at any moment stream one
     // contiguous region of every vector (whole DRAM pages) instead of grid-many 512-byte pieces
-    const int64_t r_begin = interleave ? (int64_t)blockIdx.x * ROWS : (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r_step = interleave ? (int64_t)gridDim.x * ROWS : (int64_t)ROWS;
+    const int64_t r_begin = interleave ? (int64_t)bx * ROWS : (int64_t)bx * rows_per_cta;
+    const int64_t r_step = interleave ? (int64_t)nchunks * ROWS : (int64_t)ROWS;
     const int64_t r_end = interleave ? n : (r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n);
     const int nstages = r_begin < r_end ? (int)((r_end - r_begin + r_step - 1) / r_step) : 0;
 
@@ -144,7 +154,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
             red[warp * TILE + (a * NJ + b) * 64 + g * 8 + 2 * c + 1] = acc[a][b][1];
         }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    double* out = part + (int64_t)blockIdx.x * k * m;
+    double* out = part + (int64_t)bx * k * m;
     for (int e = threadIdx.x; e < TILE; e += 128) {
         const double v = (red[e] + red[TILE + e]) + (red[2 * TILE + e] + red[3 * TILE + e]);
         const int blk = e >> 6, a = blk / NJ, b = blk % NJ;
@@ -422,6 +432,8 @@ static int gram_tma_launch(const GramTmaPlan& p, const CUtensorMap& mo, const CU
         configured = true;
     }
     dim3 grid((unsigned)p.chunks, (unsigned)p.tiles_j, (unsigned)p.tiles_i);
+    if (p.tiles_i * p.tiles_j > 1 && !g_knob[KNOB_GRAM_CHUNK_MAJOR])
+        grid = dim3((unsigned)(p.chunks * p.tiles_j * p.tiles_i), 1, 1);
     gram_tma_kernel<NI, NJ, SAME, STAGES, MINB><<<grid, GT_THREADS, SMEM, st>>>(mo, ms, m, k, n, p.rows_per_cta, p.interleave, part);
     return check_launch();
 }

@@ -43,6 +43,15 @@ for m in (48, 64, 96, 120):
             out['gram_%s_%s_ms' % (tag, name)] = round(ms, 4)
             out['gram_%s_%s_TFLOPs' % (tag, name)] = round(2.0 * n * m * m / ms / 1e9, 2)
     lib.rl_debug_set_knob(6, 0)
+    for tma in (1, 2):                       # TMA-fed ring kernel forced on the multi-tile product
+        lib.rl_debug_set_knob(0, tma)
+        wsb2 = lib.rl_gram_ws_bytes(1, m, m, n)
+        ws2 = torch.zeros(wsb2 // 8 + 8, dtype=torch.float64, device='cuda')
+        for same, tag in ((False, 'xy'), (True, 'xx')):
+            O = X if same else Y
+            ms = timeit(lambda: check(lib.rl_gram(1, X.data_ptr(), ld, m, O.data_ptr(), ld, m, n, G.data_ptr(), ws2.data_ptr(), wsb2, st)))
+            out['gram_%s_tma%d_TFLOPs' % (tag, tma)] = round(2.0 * n * m * m / ms / 1e9, 2)
+    lib.rl_debug_set_knob(0, 0)
     ref = (Y[:, :n] @ X[:, :n].T)
     check(lib.rl_gram(1, X.data_ptr(), ld, m, Y.data_ptr(), ld, m, n, G.data_ptr(), ws.data_ptr(), wsb, st))
     torch.cuda.synchronize()
