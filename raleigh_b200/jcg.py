@@ -23,9 +23,11 @@ every coefficient matrix in device memory:
   * the block buffers are rotated instead of copied: the reference moves every
     updated block through the W workspace and copies it back (:1610-1656).
 
-Supported: standard problems A x = lambda x, optional preconditioner, optional
-previously computed eigenvectors, real float32/float64.  Anything else
-(generalised problems) is handed to the reference's own `_solve`.
+Supported: standard problems A x = lambda x and generalised problems
+A x = lambda B x (B symmetric positive definite: the B-images BX, BY, BZ of the
+blocks are carried along, Gram matrices are B-Gram matrices), optional
+preconditioner, optional previously computed eigenvectors, real float32/float64.
+The product form A B x = lambda x is handed to the reference's own `_solve`.
 
 The driver talks to an `engine` (engine.py: DeviceEngine, ctypes over the C
 ABI).  The tests substitute a NumPy engine to check the control flow against
@@ -45,7 +47,7 @@ class _Fatal(Exception):
 def supported(solver, eigenvectors):
     """True when the device-resident driver can run this problem."""
     problem = solver.problem()
-    if problem.type() != 's':
+    if problem.type() not in ('s', 'g'):
         return False
     return hasattr(eigenvectors, '_rl_device_block')
 
@@ -109,10 +111,12 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     view = _SolverView(solver)
 
     opA = problem.A()
+    gen = problem.type() == 'g'
+    opB = problem.B() if gen else None
     opP = solver.preconditioner()
     eng = engine
     eng.begin(vector, m)
-    pool = _Pool(eng, 7)
+    pool = _Pool(eng, 10 if gen else 7)           # gen: the B-images of X, Y, Z as well
 
     # ---- initial block (solver.py:676-723) ---------------------------------------
     X = pool.take(m)
@@ -144,14 +148,25 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     solver.eigenvectors = eigenvectors
     Xc = eigenvectors
     nc = Xc.nvec()
+    if gen:
+        BXc = eigenvectors.clone()
+        if nc > 0:
+            opB.apply(Xc, BXc)
+        solver.eigenvectors_im = BXc
+    else:
+        BXc = Xc
     eng.reserve_constraints(nc + m)
     if nc > 0:
-        eng.gram(Xc, Xc, eng.Gc.sub(0, 0, nc, nc))
-        _project_out(eng, X, Xc, nc, m)
+        eng.gram(BXc, Xc, eng.Gc.sub(0, 0, nc, nc))
+        _project_out(eng, X, BXc, Xc, nc, m)
 
     # ---- drop linearly dependent initial vectors (solver.py:779-813) -------------
     nx = m
-    eng.gram(X, X, eng.GB.sub(0, 0, m, m))
+    BX = X
+    if gen:
+        BX = pool.take(m)
+        opB.apply(X, BX)
+    eng.gram(BX, X, eng.GB.sub(0, 0, m, m))
     eng.piv_chol(eng.GB, m, 0, 1e-2)
     dropped, ind = eng.fetch_chol(m)
     if dropped > 0:
@@ -165,19 +180,27 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         T.select(dropped, nx)
         T.fill_random()
         if nc > 0:
-            _project_out(eng, T, Xc, nc, dropped)
+            _project_out(eng, T, BXc, Xc, nc, dropped)
         T.select(m)
         pool.give(X)
         X = T
         nx = m
+        if gen:
+            opB.apply(X, BX)      # the reference gathers the kept images and projects the new ones: same block
+        else:
+            BX = X
 
     # ---- Rayleigh-Ritz in the initial space (solver.py:815-830) ------------------
     AX = pool.take(m)
     opA.apply(X, AX)
-    eng.gram(X, X, eng.GB.sub(0, 0, m, m))
+    eng.gram(BX, X, eng.GB.sub(0, 0, m, m))
     eng.gram(AX, X, eng.GA.sub(0, 0, m, m))
     eng.ritz_initial(m)                   # generalised m x m problem -> coefficients CX, Ritz values lmdx
-    X, AX = _rotate(eng, pool, (X, AX), m, m)
+    if gen:
+        X, AX, BX = _rotate(eng, pool, (X, AX, BX), m, m)
+    else:
+        X, AX = _rotate(eng, pool, (X, AX), m, m)
+        BX = X
 
     # ---- main loop ------------------------------------------------------------------
     max_iter = options.max_iter
@@ -185,7 +208,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     if max_iter < 0:
         max_iter = 100
     solver.iteration = 0
-    Z = AZ = None
+    Z = AZ = BZ = None
     nz = 0
     W = None
 
@@ -205,13 +228,14 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         nx, ix = lay.nx, lay.ix
         X.select(nx)
         AX.select(nx)
+        BX.select(nx)
 
         # Rayleigh quotients, orthonormality check, residuals (solver.py:854-974)
         eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
-        eng.gram(X, X, eng.XBX.sub(0, 0, nx, nx))
+        eng.gram(BX, X, eng.XBX.sub(0, 0, nx, nx))
         eng.ritz_check(nx)                                   # -> v_lmd, rv_err, rv_no
         W = pool.take(nx)
-        _residuals(eng, W, X, AX, Xc, nc, nx)
+        _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen)
         new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
         if verb > 2:
             print('Ritz values error: %.1e' % rv_err)
@@ -221,18 +245,19 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
                 print('restarting...')
             hist.rec = 0
             nz = 0
-            X, AX = _restart(eng, pool, opA, X, AX, nx)
+            X, AX, BX = _restart(eng, pool, opA, opB, X, AX, BX, nx)
             eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
-            eng.gram(X, X, eng.XBX.sub(0, 0, nx, nx))
+            eng.gram(BX, X, eng.XBX.sub(0, 0, nx, nx))
             eng.ritz_check(nx)
             W.select(nx)
-            _residuals(eng, W, X, AX, Xc, nc, nx)
+            _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen)
             new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
 
         hist.record_ritz_values(ix, new_lmd)
         hist.res[ix:ix + nx] = numpy.sqrt(abs(res2))
         hist.kinematic_estimates(ix, nx)
-        hist.residual_estimates(lay)
+        if not gen:                          # Lehmann / Davis-Kahan bounds: not valid for A x = lambda B x (solver.py:1009)
+            hist.residual_estimates(lay)
         hist.update_floors_and_clusters(lay, solver.iteration)
         if verb > 1:
             _print_table(solver, hist, m)
@@ -245,10 +270,10 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         # lock converged pairs (solver.py:1197-1270)
         if lcon > 0:
             _record_converged(solver, hist, ix, ix + lcon)
-            nc = _lock(eng, X, Xc, nc, 0, lcon)
+            nc = _lock(eng, X, BX, Xc, BXc, nc, 0, lcon, gen)
         if rcon > 0:
             _record_converged(solver, hist, ix + nx - rcon, ix + nx)
-            nc = _lock(eng, X, Xc, nc, nx - rcon, rcon)
+            nc = _lock(eng, X, BX, Xc, BXc, nc, nx - rcon, rcon, gen)
         solver.lcon += lcon
         solver.rcon += rcon
 
@@ -284,6 +309,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         x0 = lcon                            # first active vector inside the (compact) device blocks
         X.select(nx, x0)
         AX.select(nx, x0)
+        BX.select(nx, x0)
 
         # search directions: preconditioned residuals (solver.py:1315-1319)
         if opP is None:
@@ -301,7 +327,9 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
             Z.select(nz)
             AZ.select(nz)
             eng.gram(Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
-            eng.gram(Y, Z, eng.ZBY.sub(0, 0, nz, ny))
+            if gen:
+                BZ.select(nz)
+            eng.gram(Y, BZ if gen else Z, eng.ZBY.sub(0, 0, nz, ny))
             eng.dots(Y, Y, eng.v_s2)
             eng.dots(Z, Z, eng.v_t2)
             eng.conjugation(nz, ny)               # uses the Ritz values of the OLD window, v_lmd[0:ny]
@@ -309,19 +337,27 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
 
         # orthogonalise to X and to the locked vectors, normalise (solver.py:1360-1381)
         if nx > 0:
-            eng.gram(Y, X, eng.T1.sub(0, 0, nx, ny))
+            eng.gram(Y, BX, eng.T1.sub(0, 0, nx, ny))
             eng.update(Y, X, eng.T1.sub(0, 0, nx, ny), -1.0, 1.0)
         if nc > 0:
-            _project_out(eng, Y, Xc, nc, ny)
-        eng.dots(Y, Y, eng.v_s2)
-        eng.scale_rsqrt(Y, eng.v_s2)
+            _project_out(eng, Y, BXc, Xc, nc, ny)
+        if gen:
+            BY = pool.take(ny)
+            opB.apply(Y, BY)
+            eng.dots(BY, Y, eng.v_s2)
+            eng.scale_rsqrt(Y, eng.v_s2)
+            eng.scale_rsqrt(BY, eng.v_s2)
+        else:
+            BY = Y
+            eng.dots(Y, Y, eng.v_s2)
+            eng.scale_rsqrt(Y, eng.v_s2)
 
         # Gram matrix of (X, Y) and its pivoted Cholesky factor (solver.py:1375-1435)
         nxy = nx + ny
         if nx > 0:
             eng.copy_small(eng.XBX.sub(x0, x0, nx, nx), eng.GB.sub(0, 0, nx, nx))
-            eng.gram(Y, X, eng.GB.sub(0, nx, nx, ny))
-        eng.gram(Y, Y, eng.GB.sub(nx, nx, ny, ny))
+            eng.gram(BY, X, eng.GB.sub(0, nx, nx, ny))
+        eng.gram(BY, Y, eng.GB.sub(nx, nx, ny, ny))
         eng.mirror_upper(eng.GB, nx, ny)
         eng.piv_chol(eng.GB, nxy, nx, chol_eps)
         dropped, ind = eng.fetch_chol(nxy)
@@ -337,6 +373,13 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         eng.gather(Y, ind[nx:nxy] - nx, Yp)
         pool.give(Y)
         Y = Yp
+        if gen:
+            BYp = pool.take(ny)
+            eng.gather(BY, ind[nx:nxy] - nx, BYp)
+            pool.give(BY)
+            BY = BYp
+        else:
+            BY = Y
 
         # A-Gram matrix of (X, Y) (solver.py:1437-1454)
         AY = pool.take(ny)
@@ -379,6 +422,18 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         if nz_new > 0:
             _combine(eng, AZ, AX, AY, eng.CZ, nx, ny, nz_new)
         pool.give(AX, AY)
+        if gen:
+            BXn = pool.take(nxn)
+            _combine(eng, BXn, BX, BY, eng.CX, nx, ny, nxn)
+            if nz_new > 0:
+                if BZ is None:
+                    BZ = pool.take(nz_new)
+                BZ.select(nz_new)
+                _combine(eng, BZ, BX, BY, eng.CZ, nx, ny, nz_new)
+            pool.give(BX, BY)
+            BX = BXn
+        else:
+            BX = Xn
         X, AX = Xn, AXn
         nz = nz_new
         lay = new
@@ -470,21 +525,25 @@ def _default_criteria():
     return _Kinematic()
 
 
-def _project_out(eng, V, Xc, nc, nv):
-    """V <- V - Xc (2I - Gc) (Xc^T V)  (solver.py:774-775, 962-966, 1370-1371)."""
-    Xc.select(nc)
+def _project_out(eng, V, Against, Sub, nc, nv):
+    """V <- V - Sub (2I - Gc) (Against^T V)  (solver.py:774-775, 962-966, 1370-1371).  Standard problem:
+    Against = Sub = Xc.  Generalised: iterates and search directions are projected with Against = B Xc,
+    Sub = Xc; residuals with Against = Xc, Sub = B Xc."""
+    Against.select(nc)
+    Sub.select(nc)
     T = eng.TC.sub(0, 0, nc, nv)
     Q = eng.QC.sub(0, 0, nc, nv)
-    eng.gram(V, Xc, T)
+    eng.gram(V, Against, T)
     eng.constraint_coeffs(nc, nv)
-    eng.update(V, Xc, Q, -1.0, 1.0)
+    eng.update(V, Sub, Q, -1.0, 1.0)
 
 
-def _residuals(eng, W, X, AX, Xc, nc, nx):
-    """W = AX - X diag(lmd), projected off the locked vectors; squared norms -> v_s2."""
-    eng.residual(W, AX, X, eng.v_lmd)
+def _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen):
+    """W = AX - BX diag(lmd) (BX is X for the standard problem), projected off the locked vectors;
+    squared norms -> v_s2."""
+    eng.residual(W, AX, BX, eng.v_lmd)
     if nc > 0:
-        _project_out(eng, W, Xc, nc, nx)
+        _project_out(eng, W, Xc, BXc if gen else Xc, nc, nx)
     eng.dots(W, W, eng.v_s2)
 
 
@@ -510,17 +569,25 @@ def _combine(eng, out, X, Y, C, nx, ny, mout):
         eng.update(out, Y, C.sub(0, 0, ny, mout), 1.0, 0.0)
 
 
-def _restart(eng, pool, opA, X, AX, nx):
+def _restart(eng, pool, opA, opB, X, AX, BX, nx):
     """Loss of orthonormality among the iterates (solver.py:877-920): orthonormalise X
-    by its SVD, recompute AX and redo the Rayleigh-Ritz procedure in span(X)."""
+    by its SVD, recompute AX (and BX) and redo the Rayleigh-Ritz procedure in span(X)."""
     X.select(nx)
     X.svd()
     AX.select(nx)
     opA.apply(X, AX)
-    eng.gram(X, X, eng.GB.sub(0, 0, nx, nx))
+    if opB is not None:
+        BX.select(nx)
+        opB.apply(X, BX)
+        eng.gram(BX, X, eng.GB.sub(0, 0, nx, nx))
+    else:
+        eng.gram(X, X, eng.GB.sub(0, 0, nx, nx))
     eng.gram(AX, X, eng.GA.sub(0, 0, nx, nx))
     eng.ritz_initial(nx)
-    return _rotate(eng, pool, (X, AX), nx, nx)
+    if opB is not None:
+        return _rotate(eng, pool, (X, AX, BX), nx, nx)
+    X, AX = _rotate(eng, pool, (X, AX), nx, nx)
+    return X, AX, X
 
 
 def _record_converged(solver, hist, i0, i1):
@@ -531,18 +598,24 @@ def _record_converged(solver, hist, i0, i1):
     solver.convergence_status = numpy.concatenate((solver.convergence_status, hist.cnv[i0:i1]))
 
 
-def _lock(eng, X, Xc, nc, first, count):
-    """Append `count` iterates starting at `first` to the locked set and extend its Gram
-    matrix by the new row and column blocks (solver.py:1208-1230)."""
+def _lock(eng, X, BX, Xc, BXc, nc, first, count, gen):
+    """Append `count` iterates starting at `first` to the locked set (and their B-images to its image) and
+    extend the B-Gram matrix of the set by the new row and column blocks (solver.py:1208-1230)."""
     eng.reserve_constraints(nc + count)
     X.select(count, first)
     Xc.select(nc)
+    if gen:
+        BXc.select(nc)
     if nc > 0:
-        eng.gram(X, Xc, eng.Gc.sub(0, nc, nc, count))
+        eng.gram(X, BXc, eng.Gc.sub(0, nc, nc, count))
     Xc.append(X)
     nc_new = nc + count
     Xc.select(nc_new)
-    eng.gram(Xc, X, eng.Gc.sub(nc, 0, count, nc_new))
+    if gen:
+        BX.select(count, first)
+        BXc.append(BX)
+        BXc.select(nc_new)
+    eng.gram(BXc, X, eng.Gc.sub(nc, 0, count, nc_new))
     return nc_new
 
 

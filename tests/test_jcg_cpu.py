@@ -206,3 +206,75 @@ def test_history_shift_matches_the_reference_loops(rs):
                 reset(i)
         for k in ref:
             assert np.array_equal(getattr(h, k), ref[k]), (k, l, nl, sl, sr)
+
+
+def _mass_matrix(n, seed=0):
+    """SPD 'mass matrix' with a varying diagonal and weak nearest-neighbour coupling."""
+    import scipy.sparse as sp
+    rng = np.random.RandomState(seed)
+    d = 1.0 + rng.rand(n)
+    o = 0.1 * rng.rand(n - 1)
+    return (sp.diags(d) + sp.diags(o, 1) + sp.diags(o, -1)).tocsr()
+
+
+def _run_gen(rs, device, L, M, which, tol, block, jac=False, dtype=np.float64):
+    from raleigh_b200 import jcg
+    np.random.seed(1)
+    opt = rs.Options()
+    opt.block_size = block
+    opt.max_iter = 1000
+    opt.convergence_criteria = rs.DefaultConvergenceCriteria()
+    opt.convergence_criteria.set_error_tolerance('k eigenvector error', tol)
+    n = L.shape[0]
+    v = Vectors(n, data_type=dtype)
+    # NB: Problem(v, A, B) is the generalised problem; ANY fourth argument -- also the string 'gen' that
+    # partial_hevp.py:216 passes -- selects the product form A B x = lambda x (solver.py:241-250)
+    problem = rs.Problem(v, SparseSymmetricMatrix(L.astype(dtype)), SparseSymmetricMatrix(M.astype(dtype)))
+    assert problem.type() == 'g'
+    solver = rs.Solver(problem)
+    if jac:
+        solver.set_preconditioner(Operator(Jacobi(L)))
+    orig = rs.Solver._solve
+    if device:
+        eng = E.NumpyEngine('lapack')
+        rs.Solver._solve = lambda self, ev, o, w, e, i: jcg.solve(self, ev, o, w, e, i, eng)
+    try:
+        status = solver.solve(v, opt, which=which)
+    finally:
+        rs.Solver._solve = orig
+    return status, solver.iteration, np.array(solver.eigenvalues), v.data().copy(), solver
+
+
+GEN_CASES = [
+    ('gen left, block 8', 10, (6, 0), 1e-6, 8, False),
+    ('gen both ends', 10, (3, 3), 1e-5, 12, False),
+    ('gen largest', 10, 5, 1e-6, 8, False),
+    ('gen left, Jacobi preconditioner', 12, (6, 0), 1e-6, 8, True),
+]
+
+
+@pytest.mark.parametrize('name,N,which,tol,block,jac', GEN_CASES, ids=[c[0] for c in GEN_CASES])
+def test_driver_generalised_problem_reproduces_the_reference_iteration(rs, name, N, which, tol, block, jac):
+    """A x = lambda B x (solver.py 'gen' branches :684-689, 747-752, 949, 963, 1213-1222, 1382-1391, 1626-1641):
+    B-images of X, Y, Z and of the locked vectors carried along, B-Gram matrices, residuals A X - B X lambda."""
+    L = K.lap3d_csr(N, N, N)
+    M = _mass_matrix(L.shape[0])
+    s0, it0, lmd0, x0, _ = _run_gen(rs, False, L, M, which, tol, block, jac)
+    s1, it1, lmd1, x1, sol = _run_gen(rs, True, L, M, which, tol, block, jac)
+    assert s0 == s1 == 0
+    assert it1 == it0, (it0, it1)
+    assert len(lmd0) == len(lmd1)
+    o0, o1 = np.argsort(lmd0), np.argsort(lmd1)
+    assert np.max(np.abs(lmd1[o1] - lmd0[o0]) / np.abs(lmd0[o0])) < 1e-11
+    # B-orthonormal eigenvectors with small residuals, and the image block the reference exposes
+    Lf, Mf = L.toarray(), M.toarray()
+    x = x1.T
+    assert np.max(np.abs(x.T @ Mf @ x - np.eye(x.shape[1]))) < 1e-6
+    res = Lf @ x - (Mf @ x) * lmd1[None, :]
+    assert np.max(np.linalg.norm(res, axis=0)) < 1e-3 * np.max(np.abs(lmd1))
+    assert np.allclose(sol.eigenvectors_im.data(), (Mf @ x).T, rtol=1e-9, atol=1e-9)
+    # exact eigenvalues of the pencil
+    exact = sla.eigh(Lf, Mf, eigvals_only=True)
+    lo = np.sort(lmd1)
+    nearest = exact[np.argmin(np.abs(exact[None, :] - lo[:, None]), axis=1)]
+    assert np.max(np.abs(lo - nearest) / np.abs(nearest)) < 1e-8

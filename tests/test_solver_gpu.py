@@ -228,6 +228,52 @@ def test_device_solver_matches_verbatim_solver(gpu_backend, ref, case):
     assert np.max(res / np.abs(lam)) < 1e-4
 
 
+@pytest.mark.parametrize('N,which,block,jac', [(12, (6, 0), 8, False), (16, (4, 3), 12, False), (22, (6, 0), 16, True)])
+def test_device_solver_generalised_problem(gpu_backend, ref, N, which, block, jac):
+    """A x = lambda B x with a sparse SPD mass matrix (solver.py 'gen' branches): the device-resident driver against
+    the reference's own loop on the same backend, and against the pencil's eigenvalues."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    rs = ref
+    L = K.lap3d_csr(N, N, N)
+    n = L.shape[0]
+    rng = np.random.RandomState(0)
+    o = 0.1 * rng.rand(n - 1)
+    M = (sp.diags(1.0 + rng.rand(n)) + sp.diags(o, 1) + sp.diags(o, -1)).tocsr()
+    opA, opB = gpu_backend.SparseSymmetricMatrix(L), gpu_backend.SparseSymmetricMatrix(M)
+    T = gpu_backend.Operator(gpu_backend.DiagonalPreconditioner(L)) if jac else None
+
+    def run():
+        np.random.seed(1)
+        opt = rs.Options()
+        opt.block_size = block
+        opt.max_iter = 1000
+        opt.convergence_criteria = rs.DefaultConvergenceCriteria()
+        opt.convergence_criteria.set_error_tolerance('k eigenvector error', 1e-6)
+        v = gpu_backend.Vectors(n, data_type=np.float64)
+        problem = rs.Problem(v, opA, opB)
+        assert problem.type() == 'g'
+        solver = rs.Solver(problem)
+        if T is not None:
+            solver.set_preconditioner(T)
+        status = solver.solve(v, opt, which=which)
+        return status, solver.iteration, np.array(solver.eigenvalues), v, solver
+
+    (st0, it0, lmd0, v0, _), (st1, it1, lmd1, v1, sol) = _both_paths(gpu_backend, run)
+    assert st0 == 0 and st1 == 0 and len(lmd0) == len(lmd1)
+    assert np.max(np.abs(np.sort(lmd1) - np.sort(lmd0)) / np.abs(np.sort(lmd0))) < 1e-10, (it0, it1)
+    assert abs(it1 - it0) <= max(2, it0 // 20), (it0, it1)
+    x = v1.data().T
+    assert np.max(np.abs(x.T @ (M @ x) - np.eye(x.shape[1]))) < 1e-6
+    res = np.linalg.norm(L @ x - (M @ x) * lmd1[None, :], axis=0)
+    assert np.max(res / np.abs(lmd1)) < 1e-3
+    assert np.allclose(sol.eigenvectors_im.data(), (M @ x).T, rtol=1e-9, atol=1e-9)
+    if N <= 16:
+        exact = spla.eigsh(L.tocsc(), k=max(which[0], 1) + 2, M=M.tocsc(), sigma=0, which='LM', return_eigenvectors=False)
+        left = np.sort(lmd1)[:which[0]]
+        assert np.max(np.abs(left - np.sort(exact)[:which[0]]) / left) < 1e-8
+
+
 def test_device_solver_jacobi_preconditioned_c3_like(gpu_backend, ref):
     """Small twin of BASELINE config 3 (n >= 8192 so that the TMA Gram runs): partial_hevp with the
     Jacobi preconditioner, block 32, device-resident driver against the verbatim path."""
