@@ -24,10 +24,11 @@ every coefficient matrix in device memory:
     updated block through the W workspace and copies it back (:1610-1656).
 
 Supported: standard problems A x = lambda x and generalised problems
-A x = lambda B x (B symmetric positive definite: the B-images BX, BY, BZ of the
-blocks are carried along, Gram matrices are B-Gram matrices), optional
-preconditioner, optional previously computed eigenvectors, real float32/float64.
-The product form A B x = lambda x is handed to the reference's own `_solve`.
+A x = lambda B x and A B x = lambda x (B symmetric positive definite: the
+B-images BX, BY, BZ of the blocks are carried along, Gram matrices are B-Gram
+matrices; the product form applies A to the images and measures residuals in
+the B-norm), optional preconditioner, optional previously computed
+eigenvectors, real float32/float64.
 
 The driver talks to an `engine` (engine.py: DeviceEngine, ctypes over the C
 ABI).  The tests substitute a NumPy engine to check the control flow against
@@ -47,7 +48,7 @@ class _Fatal(Exception):
 def supported(solver, eigenvectors):
     """True when the device-resident driver can run this problem."""
     problem = solver.problem()
-    if problem.type() not in ('s', 'g'):
+    if problem.type() not in ('s', 'g', 'p'):
         return False
     return hasattr(eigenvectors, '_rl_device_block')
 
@@ -111,12 +112,14 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     view = _SolverView(solver)
 
     opA = problem.A()
-    gen = problem.type() == 'g'
-    opB = problem.B() if gen else None
+    gen = problem.type() == 'g'                   # A x = lambda B x
+    pro = problem.type() == 'p'                   # A B x = lambda x
+    hasB = gen or pro
+    opB = problem.B() if hasB else None
     opP = solver.preconditioner()
     eng = engine
     eng.begin(vector, m)
-    pool = _Pool(eng, 10 if gen else 7)           # gen: the B-images of X, Y, Z as well
+    pool = _Pool(eng, 10 if hasB else 7)          # with B: the B-images of X, Y, Z as well
 
     # ---- initial block (solver.py:676-723) ---------------------------------------
     X = pool.take(m)
@@ -148,7 +151,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     solver.eigenvectors = eigenvectors
     Xc = eigenvectors
     nc = Xc.nvec()
-    if gen:
+    if hasB:
         BXc = eigenvectors.clone()
         if nc > 0:
             opB.apply(Xc, BXc)
@@ -163,7 +166,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
     # ---- drop linearly dependent initial vectors (solver.py:779-813) -------------
     nx = m
     BX = X
-    if gen:
+    if hasB:
         BX = pool.take(m)
         opB.apply(X, BX)
     eng.gram(BX, X, eng.GB.sub(0, 0, m, m))
@@ -185,18 +188,18 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         pool.give(X)
         X = T
         nx = m
-        if gen:
+        if hasB:
             opB.apply(X, BX)      # the reference gathers the kept images and projects the new ones: same block
         else:
             BX = X
 
     # ---- Rayleigh-Ritz in the initial space (solver.py:815-830) ------------------
     AX = pool.take(m)
-    opA.apply(X, AX)
+    opA.apply(BX if pro else X, AX)
     eng.gram(BX, X, eng.GB.sub(0, 0, m, m))
-    eng.gram(AX, X, eng.GA.sub(0, 0, m, m))
+    eng.gram(AX, BX if pro else X, eng.GA.sub(0, 0, m, m))
     eng.ritz_initial(m)                   # generalised m x m problem -> coefficients CX, Ritz values lmdx
-    if gen:
+    if hasB:
         X, AX, BX = _rotate(eng, pool, (X, AX, BX), m, m)
     else:
         X, AX = _rotate(eng, pool, (X, AX), m, m)
@@ -231,11 +234,12 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         BX.select(nx)
 
         # Rayleigh quotients, orthonormality check, residuals (solver.py:854-974)
-        eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
+        eng.gram(AX, BX if pro else X, eng.XAX.sub(0, 0, nx, nx))
         eng.gram(BX, X, eng.XBX.sub(0, 0, nx, nx))
         eng.ritz_check(nx)                                   # -> v_lmd, rv_err, rv_no
         W = pool.take(nx)
-        _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen)
+        BW = pool.take(nx) if pro else None                  # product form: B-image of the residuals
+        _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB if pro else None)
         new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
         if verb > 2:
             print('Ritz values error: %.1e' % rv_err)
@@ -245,12 +249,12 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
                 print('restarting...')
             hist.rec = 0
             nz = 0
-            X, AX, BX = _restart(eng, pool, opA, opB, X, AX, BX, nx)
-            eng.gram(AX, X, eng.XAX.sub(0, 0, nx, nx))
+            X, AX, BX = _restart(eng, pool, opA, opB, X, AX, BX, nx, pro)
+            eng.gram(AX, BX if pro else X, eng.XAX.sub(0, 0, nx, nx))
             eng.gram(BX, X, eng.XBX.sub(0, 0, nx, nx))
             eng.ritz_check(nx)
             W.select(nx)
-            _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen)
+            _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB if pro else None)
             new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
 
         hist.record_ritz_values(ix, new_lmd)
@@ -270,10 +274,10 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         # lock converged pairs (solver.py:1197-1270)
         if lcon > 0:
             _record_converged(solver, hist, ix, ix + lcon)
-            nc = _lock(eng, X, BX, Xc, BXc, nc, 0, lcon, gen)
+            nc = _lock(eng, X, BX, Xc, BXc, nc, 0, lcon, hasB)
         if rcon > 0:
             _record_converged(solver, hist, ix + nx - rcon, ix + nx)
-            nc = _lock(eng, X, BX, Xc, BXc, nc, nx - rcon, rcon, gen)
+            nc = _lock(eng, X, BX, Xc, BXc, nc, nx - rcon, rcon, hasB)
         solver.lcon += lcon
         solver.rcon += rcon
 
@@ -312,7 +316,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         BX.select(nx, x0)
 
         # search directions: preconditioned residuals (solver.py:1315-1319)
-        if opP is None:
+        if opP is None or pro:               # product form: no preconditioning step (solver.py:1315)
             Y = W
         else:
             Y = pool.take(ny)
@@ -326,22 +330,39 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         if nz > 0:
             Z.select(nz)
             AZ.select(nz)
-            eng.gram(Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
-            if gen:
+            if hasB:
                 BZ.select(nz)
-            eng.gram(Y, BZ if gen else Z, eng.ZBY.sub(0, 0, nz, ny))
+            if pro:
+                BW.select(ny)
+            eng.gram(BW if pro else Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
+            eng.gram(Y, BZ if hasB else Z, eng.ZBY.sub(0, 0, nz, ny))
             eng.dots(Y, Y, eng.v_s2)
             eng.dots(Z, Z, eng.v_t2)
             eng.conjugation(nz, ny)               # uses the Ritz values of the OLD window, v_lmd[0:ny]
             eng.update(Y, Z, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
+            if pro:
+                eng.update(BW, BZ, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
 
         # orthogonalise to X and to the locked vectors, normalise (solver.py:1360-1381)
+        if pro:
+            BW.select(ny)
         if nx > 0:
             eng.gram(Y, BX, eng.T1.sub(0, 0, nx, ny))
             eng.update(Y, X, eng.T1.sub(0, 0, nx, ny), -1.0, 1.0)
+            if pro:
+                eng.update(BW, BX, eng.T1.sub(0, 0, nx, ny), -1.0, 1.0)
         if nc > 0:
             _project_out(eng, Y, BXc, Xc, nc, ny)
-        if gen:
+            if pro:                              # same coefficients, applied to the image block
+                BXc.select(nc)
+                eng.update(BW, BXc, eng.QC.sub(0, 0, nc, ny), -1.0, 1.0)
+        if pro:
+            BY = BW
+            BW = None
+            eng.dots(BY, Y, eng.v_s2)
+            eng.scale_rsqrt(Y, eng.v_s2)
+            eng.scale_rsqrt(BY, eng.v_s2)
+        elif gen:
             BY = pool.take(ny)
             opB.apply(Y, BY)
             eng.dots(BY, Y, eng.v_s2)
@@ -373,7 +394,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         eng.gather(Y, ind[nx:nxy] - nx, Yp)
         pool.give(Y)
         Y = Yp
-        if gen:
+        if hasB:
             BYp = pool.take(ny)
             eng.gather(BY, ind[nx:nxy] - nx, BYp)
             pool.give(BY)
@@ -383,11 +404,11 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
 
         # A-Gram matrix of (X, Y) (solver.py:1437-1454)
         AY = pool.take(ny)
-        opA.apply(Y, AY)
+        opA.apply(BY if pro else Y, AY)
         if nx > 0:
             eng.copy_small(eng.XAX.sub(x0, x0, nx, nx), eng.GA.sub(0, 0, nx, nx))
-            eng.gram(AY, X, eng.GA.sub(0, nx, nx, ny))
-        eng.gram(AY, Y, eng.GA.sub(nx, nx, ny, ny))
+            eng.gram(AY, BX if pro else X, eng.GA.sub(0, nx, nx, ny))
+        eng.gram(AY, BY if pro else Y, eng.GA.sub(nx, nx, ny, ny))
         eng.mirror_upper(eng.GA, nx, ny)
 
         # next block layout: integers only, known before the Ritz problem is solved
@@ -422,7 +443,7 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         if nz_new > 0:
             _combine(eng, AZ, AX, AY, eng.CZ, nx, ny, nz_new)
         pool.give(AX, AY)
-        if gen:
+        if hasB:
             BXn = pool.take(nxn)
             _combine(eng, BXn, BX, BY, eng.CX, nx, ny, nxn)
             if nz_new > 0:
@@ -538,13 +559,22 @@ def _project_out(eng, V, Against, Sub, nc, nv):
     eng.update(V, Sub, Q, -1.0, 1.0)
 
 
-def _residuals(eng, W, BX, AX, Xc, BXc, nc, nx, gen):
-    """W = AX - BX diag(lmd) (BX is X for the standard problem), projected off the locked vectors;
-    squared norms -> v_s2."""
-    eng.residual(W, AX, BX, eng.v_lmd)
+def _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB_pro):
+    """Residuals projected off the locked vectors, squared norms -> v_s2 (solver.py:942-974).
+    std: W = A X - X lmd, W -= Xc Gci Xc^T W.   gen: W = A X - B X lmd, W -= B Xc Gci Xc^T W.
+    pro: W = A B X - X lmd, W -= Xc Gci (B Xc)^T W, BW = B W, norms in the B inner product."""
+    eng.residual(W, AX, BX if gen else X, eng.v_lmd)
     if nc > 0:
-        _project_out(eng, W, Xc, BXc if gen else Xc, nc, nx)
-    eng.dots(W, W, eng.v_s2)
+        if opB_pro is not None:
+            _project_out(eng, W, BXc, Xc, nc, nx)
+        else:
+            _project_out(eng, W, Xc, BXc if gen else Xc, nc, nx)
+    if opB_pro is not None:
+        BW.select(nx)
+        opB_pro.apply(W, BW)
+        eng.dots(BW, W, eng.v_s2)
+    else:
+        eng.dots(W, W, eng.v_s2)
 
 
 def _rotate(eng, pool, blocks, k, mout):
@@ -569,20 +599,20 @@ def _combine(eng, out, X, Y, C, nx, ny, mout):
         eng.update(out, Y, C.sub(0, 0, ny, mout), 1.0, 0.0)
 
 
-def _restart(eng, pool, opA, opB, X, AX, BX, nx):
+def _restart(eng, pool, opA, opB, X, AX, BX, nx, pro=False):
     """Loss of orthonormality among the iterates (solver.py:877-920): orthonormalise X
     by its SVD, recompute AX (and BX) and redo the Rayleigh-Ritz procedure in span(X)."""
     X.select(nx)
     X.svd()
     AX.select(nx)
-    opA.apply(X, AX)
     if opB is not None:
         BX.select(nx)
         opB.apply(X, BX)
         eng.gram(BX, X, eng.GB.sub(0, 0, nx, nx))
     else:
         eng.gram(X, X, eng.GB.sub(0, 0, nx, nx))
-    eng.gram(AX, X, eng.GA.sub(0, 0, nx, nx))
+    opA.apply(BX if pro else X, AX)
+    eng.gram(AX, BX if pro else X, eng.GA.sub(0, 0, nx, nx))
     eng.ritz_initial(nx)
     if opB is not None:
         return _rotate(eng, pool, (X, AX, BX), nx, nx)

@@ -217,7 +217,7 @@ def _mass_matrix(n, seed=0):
     return (sp.diags(d) + sp.diags(o, 1) + sp.diags(o, -1)).tocsr()
 
 
-def _run_gen(rs, device, L, M, which, tol, block, jac=False, dtype=np.float64):
+def _run_gen(rs, device, L, M, which, tol, block, jac=False, dtype=np.float64, product=False):
     from raleigh_b200 import jcg
     np.random.seed(1)
     opt = rs.Options()
@@ -229,8 +229,12 @@ def _run_gen(rs, device, L, M, which, tol, block, jac=False, dtype=np.float64):
     v = Vectors(n, data_type=dtype)
     # NB: Problem(v, A, B) is the generalised problem; ANY fourth argument -- also the string 'gen' that
     # partial_hevp.py:216 passes -- selects the product form A B x = lambda x (solver.py:241-250)
-    problem = rs.Problem(v, SparseSymmetricMatrix(L.astype(dtype)), SparseSymmetricMatrix(M.astype(dtype)))
-    assert problem.type() == 'g'
+    if product:
+        problem = rs.Problem(v, SparseSymmetricMatrix(L.astype(dtype)), SparseSymmetricMatrix(M.astype(dtype)), 'pro')
+        assert problem.type() == 'p'
+    else:
+        problem = rs.Problem(v, SparseSymmetricMatrix(L.astype(dtype)), SparseSymmetricMatrix(M.astype(dtype)))
+        assert problem.type() == 'g'
     solver = rs.Solver(problem)
     if jac:
         solver.set_preconditioner(Operator(Jacobi(L)))
@@ -275,6 +279,37 @@ def test_driver_generalised_problem_reproduces_the_reference_iteration(rs, name,
     assert np.allclose(sol.eigenvectors_im.data(), (Mf @ x).T, rtol=1e-9, atol=1e-9)
     # exact eigenvalues of the pencil
     exact = sla.eigh(Lf, Mf, eigvals_only=True)
+    lo = np.sort(lmd1)
+    nearest = exact[np.argmin(np.abs(exact[None, :] - lo[:, None]), axis=1)]
+    assert np.max(np.abs(lo - nearest) / np.abs(nearest)) < 1e-8
+
+
+PRO_CASES = [
+    ('pro left, block 8', 10, (6, 0), 1e-6, 8),
+    ('pro both ends', 10, (3, 3), 1e-5, 12),
+    ('pro largest', 8, 4, 1e-6, 8),
+]
+
+
+@pytest.mark.parametrize('name,N,which,tol,block', PRO_CASES, ids=[c[0] for c in PRO_CASES])
+def test_driver_product_problem_reproduces_the_reference_iteration(rs, name, N, which, tol, block):
+    """A B x = lambda x (solver.py 'pro' branches: A applied to the B-images, residuals A B X - X lambda measured in
+    the B-norm, no preconditioning step, image block updated alongside the search directions)."""
+    L = K.lap3d_csr(N, N, N)
+    M = _mass_matrix(L.shape[0])
+    s0, it0, lmd0, x0, _ = _run_gen(rs, False, L, M, which, tol, block, product=True)
+    s1, it1, lmd1, x1, sol = _run_gen(rs, True, L, M, which, tol, block, product=True)
+    assert s0 == s1 == 0
+    assert it1 == it0, (it0, it1)
+    assert len(lmd0) == len(lmd1)
+    o0, o1 = np.argsort(lmd0), np.argsort(lmd1)
+    assert np.max(np.abs(lmd1[o1] - lmd0[o0]) / np.abs(lmd0[o0])) < 1e-11
+    Lf, Mf = L.toarray(), M.toarray()
+    x = x1.T
+    assert np.max(np.abs(x.T @ Mf @ x - np.eye(x.shape[1]))) < 1e-6
+    res = Lf @ (Mf @ x) - x * lmd1[None, :]
+    assert np.max(np.linalg.norm(res, axis=0)) < 1e-3 * np.max(np.abs(lmd1))
+    exact = np.sort(np.linalg.eigvals(Lf @ Mf).real)
     lo = np.sort(lmd1)
     nearest = exact[np.argmin(np.abs(exact[None, :] - lo[:, None]), axis=1)]
     assert np.max(np.abs(lo - nearest) / np.abs(nearest)) < 1e-8

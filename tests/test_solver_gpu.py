@@ -274,6 +274,34 @@ def test_device_solver_generalised_problem(gpu_backend, ref, N, which, block, ja
         assert np.max(np.abs(left - np.sort(exact)[:which[0]]) / left) < 1e-8
 
 
+def test_device_solver_partial_hevp_with_mass_matrix(gpu_backend, ref):
+    """partial_hevp(A, B, T=...) (partial_hevp.py:202-224): `Problem(v, A, B, 'gen')` -- whose fourth argument selects
+    the PRODUCT form A B x = lambda x (solver.py:241-250) -- through the device-resident driver and through the
+    reference's own loop: same eigenvalues, which are eigenvalues of A B."""
+    import scipy.sparse as sp
+    from raleigh.interfaces.partial_hevp import partial_hevp
+    L = K.lap3d_csr(12, 12, 12)
+    n = L.shape[0]
+    rng = np.random.RandomState(0)
+    o = 0.1 * rng.rand(n - 1)
+    M = (sp.diags(1.0 + rng.rand(n)) + sp.diags(o, 1) + sp.diags(o, -1)).tocsr()
+    T = gpu_backend.DiagonalPreconditioner(L)
+
+    def run():
+        np.random.seed(1)
+        opt = ref.Options()
+        opt.block_size = 8
+        opt.max_iter = 1000
+        return partial_hevp(L, B=M, T=T, which=5, tol=1e-6, verb=-1, opt=opt)
+
+    (lmd0, x0, st0), (lmd1, x1, st1) = _both_paths(gpu_backend, run)
+    assert st0 == 0 and st1 == 0 and len(lmd0) >= 5 and len(lmd1) >= 5      # every converged pair is returned
+    k = min(len(lmd0), len(lmd1))
+    assert np.max(np.abs(lmd1[:k] - lmd0[:k]) / np.abs(lmd0[:k])) < 1e-10
+    res = L @ (M @ x1) - x1 * lmd1[None, :]
+    assert np.max(np.linalg.norm(res, axis=0) / np.abs(lmd1)) < 1e-3
+
+
 def test_device_solver_jacobi_preconditioned_c3_like(gpu_backend, ref):
     """Small twin of BASELINE config 3 (n >= 8192 so that the TMA Gram runs): partial_hevp with the
     Jacobi preconditioner, block 32, device-resident driver against the verbatim path."""
