@@ -2,7 +2,9 @@
 // memory, and the staging rings used by the *_h (host-array) entry points.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -90,6 +92,150 @@ static int check_owner_device() {
     if (cudaGetDevice(&dev) != cudaSuccess) return RL_E_ARG;
     if (g_owner_device < 0) g_owner_device = dev;
     return dev == g_owner_device ? 0 : RL_E_ARG;
+}
+
+// ---- big copies between PAGEABLE host memory and the device ---------------------------------------------------
+// cudaMemcpy from / to pageable memory is staged by the driver at ~11 GB/s host-to-device and ~4 GB/s device-to-host
+// on this box (config 5: 17 GB of chunks = 1.56 of 2.8 s; the 1 GB left factor coming back = 0.27 s).  Copies of
+// 32 MB and more go through two pinned 64 MB staging buffers instead: a few host threads move one piece between the
+// user's array and a staging buffer while the DMA engine moves the previous piece at PCIe speed.
+// RALEIGH_B200_COPY_THREADS overrides the thread count (default: the process's share of the cores, at most 8).
+constexpr size_t kStageBytes = size_t(64) << 20;
+constexpr size_t kStagedCopyMin = size_t(32) << 20;
+struct CopyStage { char* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2]; bool ready = false; };
+static CopyStage g_stage;
+
+static int copy_threads() {
+    static int n = 0;
+    if (n) return n;
+    const char* e = getenv("RALEIGH_B200_COPY_THREADS");
+    if (e && atoi(e) > 0) { n = atoi(e); return n; }
+    unsigned hc = std::thread::hardware_concurrency();
+    int procs = 1;
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    if (lw && atoi(lw) > 0) procs = atoi(lw);
+    int t = (int)(hc ? hc : 4) / procs;
+    n = t < 1 ? 1 : (t > 8 ? 8 : t);
+    return n;
+}
+
+static bool big_pageable(const void* host, size_t bytes) {
+    if (bytes < kStagedCopyMin || g_knob[KNOB_COPY_DIRECT]) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+static void rows_copy(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
+    const int nt = copy_threads();
+    auto work = [=](size_t r0, size_t r1) {
+        if (dpitch == width && spitch == width) { memcpy(dst + r0 * width, src + r0 * width, (r1 - r0) * width); return; }
+        for (size_t r = r0; r < r1; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
+    };
+    if (rows == 1 && nt > 1) {          // one long row: split it by bytes
+        std::vector<std::thread> th;
+        const size_t per = (width / nt + 4095) & ~size_t(4095);
+        for (int t = 0; t < nt; ++t) {
+            const size_t b0 = (size_t)t * per, b1 = b0 + per < width ? b0 + per : width;
+            if (b0 >= width) break;
+            th.emplace_back([=] { memcpy(dst + b0, src + b0, b1 - b0); });
+        }
+        for (auto& x : th) x.join();
+        return;
+    }
+    if (nt <= 1 || rows < 2) { work(0, rows); return; }
+    std::vector<std::thread> th;
+    const size_t per = (rows + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const size_t r0 = (size_t)t * per, r1 = r0 + per < rows ? r0 + per : rows;
+        if (r0 >= rows) break;
+        th.emplace_back(work, r0, r1);
+    }
+    for (auto& x : th) x.join();
+}
+
+// to_device: dst device (dpitch), src host (spitch); else dst host, src device.  Returns after the last byte moved.
+static int staged_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                          bool to_device, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_stage.ready) {
+        for (int i = 0; i < 2; ++i) {
+            RL_CUDA(cudaHostAlloc((void**)&g_stage.buf[i], kStageBytes, cudaHostAllocPortable));
+            RL_CUDA(cudaEventCreateWithFlags(&g_stage.ev[i], cudaEventDisableTiming));
+        }
+        g_stage.ready = true;
+    }
+    // pieces: whole rows when a row fits the staging buffer, else byte ranges of the single long row
+    if (height != 1 && width > kStageBytes) {          // rows longer than a staging buffer: leave it to the driver
+        RL_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height,
+                                  to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+        return (int)cudaStreamSynchronize(st);
+    }
+    if (height == 1) {
+        size_t done = 0;
+        int i = 0;
+        size_t prev_bytes = 0, prev_off = 0;
+        for (; done < width; ++i) {
+            const int b = i & 1;
+            const size_t len = width - done < kStageBytes ? width - done : kStageBytes;
+            if (to_device) {
+                if (i >= 2) RL_CUDA(cudaEventSynchronize(g_stage.ev[b]));
+                rows_copy(g_stage.buf[b], len, (const char*)src + done, len, len, 1);
+                RL_CUDA(cudaMemcpyAsync((char*)dst + done, g_stage.buf[b], len, cudaMemcpyHostToDevice, st));
+                RL_CUDA(cudaEventRecord(g_stage.ev[b], st));
+            } else {
+                RL_CUDA(cudaMemcpyAsync(g_stage.buf[b], (const char*)src + done, len, cudaMemcpyDeviceToHost, st));
+                RL_CUDA(cudaEventRecord(g_stage.ev[b], st));
+                if (i >= 1) {
+                    RL_CUDA(cudaEventSynchronize(g_stage.ev[b ^ 1]));
+                    rows_copy((char*)dst + prev_off, prev_bytes, g_stage.buf[b ^ 1], prev_bytes, prev_bytes, 1);
+                }
+                prev_bytes = len; prev_off = done;
+            }
+            done += len;
+        }
+        if (to_device) {
+            RL_CUDA(cudaEventSynchronize(g_stage.ev[0]));
+            if (i > 1) RL_CUDA(cudaEventSynchronize(g_stage.ev[1]));
+        } else {
+            const int b = (i - 1) & 1;
+            RL_CUDA(cudaEventSynchronize(g_stage.ev[b]));
+            rows_copy((char*)dst + prev_off, prev_bytes, g_stage.buf[b], prev_bytes, prev_bytes, 1);
+        }
+        return 0;
+    }
+    const size_t rpp = kStageBytes / width;          // rows per piece (>= 1 here)
+    size_t prev_r0 = 0, prev_rows = 0;
+    int i = 0;
+    for (size_t r0 = 0; r0 < height; r0 += rpp, ++i) {
+        const int b = i & 1;
+        const size_t rows = height - r0 < rpp ? height - r0 : rpp;
+        if (to_device) {
+            if (i >= 2) RL_CUDA(cudaEventSynchronize(g_stage.ev[b]));
+            rows_copy(g_stage.buf[b], width, (const char*)src + r0 * spitch, spitch, width, rows);
+            RL_CUDA(cudaMemcpy2DAsync((char*)dst + r0 * dpitch, dpitch, g_stage.buf[b], width, width, rows,
+                                      cudaMemcpyHostToDevice, st));
+            RL_CUDA(cudaEventRecord(g_stage.ev[b], st));
+        } else {
+            RL_CUDA(cudaMemcpy2DAsync(g_stage.buf[b], width, (const char*)src + r0 * spitch, spitch, width, rows,
+                                      cudaMemcpyDeviceToHost, st));
+            RL_CUDA(cudaEventRecord(g_stage.ev[b], st));
+            if (i >= 1) {
+                RL_CUDA(cudaEventSynchronize(g_stage.ev[b ^ 1]));
+                rows_copy((char*)dst + prev_r0 * dpitch, dpitch, g_stage.buf[b ^ 1], width, width, prev_rows);
+            }
+            prev_r0 = r0; prev_rows = rows;
+        }
+    }
+    if (to_device) {
+        RL_CUDA(cudaEventSynchronize(g_stage.ev[0]));
+        if (i > 1) RL_CUDA(cudaEventSynchronize(g_stage.ev[1]));
+    } else {
+        const int b = (i - 1) & 1;
+        RL_CUDA(cudaEventSynchronize(g_stage.ev[b]));
+        rows_copy((char*)dst + prev_r0 * dpitch, dpitch, g_stage.buf[b], width, width, prev_rows);
+    }
+    return 0;
 }
 
 int staging_acquire(size_t bytes, void** pinned, void** dev) {
@@ -217,22 +363,28 @@ int rl_memset(void* ptr, int value, size_t bytes, void* stream) {
 }
 int rl_h2d(void* dst, const void* src_h, size_t bytes, void* stream) {
     if (bytes == 0) return 0;
+    if (big_pageable(src_h, bytes)) return staged_copy_2d(dst, bytes, src_h, bytes, bytes, 1, true, as_stream(stream));
     return (int)cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, as_stream(stream));
 }
 int rl_d2h(void* dst_h, const void* src, size_t bytes, void* stream) {
     if (bytes == 0) return 0;
+    if (big_pageable(dst_h, bytes)) return staged_copy_2d(dst_h, bytes, src, bytes, bytes, 1, false, as_stream(stream));
     RL_CUDA(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
     return (int)cudaStreamSynchronize(as_stream(stream));
 }
 int rl_h2d_2d(void* dst, size_t dpitch, const void* src_h, size_t spitch, size_t width,
               size_t height, void* stream) {
     if (width == 0 || height == 0) return 0;
+    if (big_pageable(src_h, width * height))
+        return staged_copy_2d(dst, dpitch, src_h, spitch, width, height, true, as_stream(stream));
     return (int)cudaMemcpy2DAsync(dst, dpitch, src_h, spitch, width, height,
                                   cudaMemcpyHostToDevice, as_stream(stream));
 }
 int rl_d2h_2d(void* dst_h, size_t dpitch, const void* src, size_t spitch, size_t width,
               size_t height, void* stream) {
     if (width == 0 || height == 0) return 0;
+    if (big_pageable(dst_h, width * height))
+        return staged_copy_2d(dst_h, dpitch, src, spitch, width, height, false, as_stream(stream));
     RL_CUDA(cudaMemcpy2DAsync(dst_h, dpitch, src, spitch, width, height,
                               cudaMemcpyDeviceToHost, as_stream(stream)));
     return (int)cudaStreamSynchronize(as_stream(stream));

@@ -23,6 +23,7 @@ ap.add_argument('--chunk', type=int, default=65536)
 ap.add_argument('--rank', type=int, default=256)
 ap.add_argument('--tol', type=float, default=0.05)
 ap.add_argument('--cpu', action='store_true')
+ap.add_argument('--host-profile', action='store_true', help='cProfile of a second run (rank 0): where the host time goes')
 args = ap.parse_args()
 
 world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -62,7 +63,7 @@ if world > 1:
     both = torch.stack((num, den)); tdist.all_reduce(both); num, den = both[0], both[1]
     tmax = torch.tensor([dt], device='cuda'); tdist.all_reduce(tmax, op=tdist.ReduceOp.MAX); dt = float(tmax.item())
 ef = float(torch.sqrt(num / den).item())
-line = {'config': 'C5 (%d GPU%s, samples partitioned): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % (world, '' if world == 1 else 's', args.rows, args.cols, args.chunk * world, args.tol),
+line = {'config': 'C5 (%s): incremental PCA of %dx%d fp32 in %d-row chunks, tol %.2g' % ('single GPU' if world == 1 else '%d GPUs, samples partitioned' % world, args.rows, args.cols, args.chunk * world, args.tol),
         'gpu_s': round(dt, 3), 'components': int(comps.shape[0]), 'pca_error_frobenius': ef,
         'device_ms': round(sum(v_['ms'] for v_ in prof.values()), 1),
         'kernels': {k: {'count': v_['count'], 'ms': round(v_['ms'], 1)} for k, v_ in prof.items()}}
@@ -74,6 +75,14 @@ if args.cpu:
     line['cpu_components'] = int(comps2.shape[0])
 if rank == 0:
     print(json.dumps(line), flush=True)
+if args.host_profile and world == 1:
+    import cProfile, pstats
+    with threadpool_limits(limits=1):
+        np.random.seed(1)
+        pr = cProfile.Profile(); pr.enable()
+        pca(A, tol=args.tol, batch_size=args.chunk, arch='gpu!', opt=Options())
+        torch.cuda.synchronize(); pr.disable()
+    pstats.Stats(pr).sort_stats('tottime').print_stats(30)
 if world > 1:
     tdist.barrier()
     tdist.destroy_process_group()

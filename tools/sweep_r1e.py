@@ -36,7 +36,6 @@ from microbench import timeit, peak_gbs  # noqa: E402
 from run_c4 import lap3d_slab  # noqa: E402
 
 KNOB_GRAM_TMA, KNOB_SPMM_CARVEOUT, KNOB_SPMM_WPS, KNOB_SPMM_PF, KNOB_GRAM_INTERLEAVE, KNOB_GRAM_WAVES = 0, 1, 2, 3, 4, 5
-KNOB_SPMM_WINDOW, KNOB_SPMM_WIN_CHUNKS = 6, 7
 GRAM_MODES = [(-1, 0), (0, 0), (3, 4), (3, 8), (3, 16), (3, 32)]      # (TMA mode, CTAs per SM slot)
 OUT = [None]
 
