@@ -353,6 +353,24 @@ def hook_device_lra_update():
 
     cls.update = update
 
+    if getattr(cls, '_reference_icompute', None) is None:
+        cls._reference_icompute = cls.icompute
+
+        def icompute(self, matrix, batch_size, *args, **kwargs):
+            # chunked run: the chunks are row slices of `matrix` taken in order (lra.py:403-421) -- let the Matrix
+            # constructor upload the next one in the background while this one is processed (vectors._ChunkPrefetch)
+            from . import vectors
+            arch = kwargs.get('arch', 'cpu')
+            saved = vectors.CHUNK_PREFETCH
+            vectors.CHUNK_PREFETCH = bool(DEVICE_SOLVER and isinstance(arch, str) and arch[:3] == 'gpu')
+            try:
+                return cls._reference_icompute(self, matrix, batch_size, *args, **kwargs)
+            finally:
+                vectors.CHUNK_PREFETCH = saved
+                vectors._chunk_prefetch.drop()
+
+        cls.icompute = icompute
+
 
 def install(reference_path=None, sparse=True, dense=True):
     """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.

@@ -104,6 +104,7 @@ constexpr size_t kStageBytes = size_t(64) << 20;
 constexpr size_t kStagedCopyMin = size_t(32) << 20;
 struct CopyStage { char* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2]; bool ready = false; };
 static CopyStage g_stage;
+static std::mutex g_stage_mu;          // its own lock: a background chunk upload must not stall the *_h entry points
 
 static int copy_threads() {
     static int n = 0;
@@ -157,7 +158,7 @@ static void rows_copy(char* dst, size_t dpitch, const char* src, size_t spitch, 
 // to_device: dst device (dpitch), src host (spitch); else dst host, src device.  Returns after the last byte moved.
 static int staged_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
                           bool to_device, cudaStream_t st) {
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_stage_mu);
     if (!g_stage.ready) {
         for (int i = 0; i < 2; ++i) {
             RL_CUDA(cudaHostAlloc((void**)&g_stage.buf[i], kStageBytes, cudaHostAllocPortable));

@@ -658,6 +658,86 @@ class Vectors:
         return block_svd(self)
 
 
+# ---- input pipeline for chunked runs ------------------------------------------------
+# lra.icompute (lra.py:381-422) hands `matrix[first:next, :]` to AMatrix chunk after chunk; each construction is a
+# blocking upload of ~1 GB.  While compat's hooked icompute runs (it is the caller that promises sequential, read-only
+# access to the big array) the constructor of chunk i starts a background upload of the rows that FOLLOW it, on a
+# side stream, and the constructor of chunk i+1 adopts that buffer if it is asked for exactly those rows.
+CHUNK_PREFETCH = False
+CHUNK_PREFETCH_MIN_BYTES = 64 << 20
+
+
+class _ChunkPrefetch:
+    def __init__(self):
+        self._key = None          # (address, rows, cols, itemsize, ld_bytes)
+        self._buf = None
+        self._thread = None
+        self._stream = None
+        self._error = None
+
+    def _join(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+
+    def drop(self):
+        self._join()
+        self._key = self._buf = self._error = None
+
+    def claim(self, a, ld_bytes):
+        """Device buffer holding `a` if the pending prefetch is for exactly this block, else None."""
+        if self._key is None:
+            return None
+        key = (a.ctypes.data, a.shape[0], a.shape[1], a.itemsize, ld_bytes)
+        self._join()
+        buf, ok = self._buf, (self._key == key and self._error is None)
+        self._key = self._buf = self._error = None
+        return buf if ok else None
+
+    def start_next(self, a, ld_bytes):
+        """`a` is rows [r0, r1) of a bigger C-contiguous array: upload rows [r1, r1 + (r1 - r0)) (or what is left)."""
+        base = a.base
+        if base is None or not isinstance(base, numpy.ndarray) or base.ndim != 2 or not base.flags['C_CONTIGUOUS'] \
+                or base.shape[1] != a.shape[1] or base.dtype != a.dtype or a.nbytes < CHUNK_PREFETCH_MIN_BYTES:
+            return
+        row_bytes = a.shape[1] * a.itemsize
+        off = a.ctypes.data - base.ctypes.data
+        if off < 0 or off % row_bytes:
+            return
+        r1 = off // row_bytes + a.shape[0]
+        rows = min(a.shape[0], base.shape[0] - r1)
+        if rows < 1:
+            return
+        nxt = base[r1:r1 + rows]
+        import threading
+        import torch
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        buf = dev.Buffer(rows * ld_bytes)
+        # the allocator may hand out memory that work already queued on the main stream still reads
+        self._stream.wait_stream(torch.cuda.current_stream())
+        stream_handle = self._stream.cuda_stream
+        self._key = (nxt.ctypes.data, rows, nxt.shape[1], nxt.itemsize, ld_bytes)
+        self._buf = buf
+        self._error = None
+        device_index = torch.cuda.current_device()
+
+        def work():
+            try:
+                torch.cuda.set_device(device_index)
+                row = nxt.shape[1] * nxt.itemsize
+                check(lib.rl_h2d_2d(buf.ptr, ld_bytes, dev.host_ptr(nxt), row, row, rows, stream_handle))
+                check(lib.rl_sync_stream(stream_handle))
+            except Exception as e:      # the claim falls back to a normal upload
+                self._error = e
+
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+
+_chunk_prefetch = _ChunkPrefetch()
+
+
 class SampleVectors:
     """The rows of a SAMPLE-PARTITIONED data matrix viewed as vectors (AMatrix.as_vectors(), dense_matrix.py:40-43,
     used by lra.update, lra.py:182-260): every process holds all components of SOME of the vectors.  The object
@@ -807,8 +887,14 @@ class Matrix:
             w = stored.itemsize
             self._ld = dev.padded_ld(cols, w)
             self._base = 0
-            self._buf = dev.Buffer(max(rows, 1) * self._ld * w)
-            dev.upload_2d(self._buf.ptr, self._ld * w, stored)
+            got = _chunk_prefetch.claim(stored, self._ld * w) if CHUNK_PREFETCH else None
+            if got is not None:
+                self._buf = got                               # uploaded in the background during the previous chunk
+            else:
+                self._buf = dev.Buffer(max(rows, 1) * self._ld * w)
+                dev.upload_2d(self._buf.ptr, self._ld * w, stored)
+            if CHUNK_PREFETCH:
+                _chunk_prefetch.start_next(stored, self._ld * w)
             if arg.nbytes >= MINMAX_ON_DEVICE_BYTES:
                 # AMatrix scans this same host array with numpy.amin / amax right after building
                 # the Matrix (dense_matrix.py:32-34): let compat's proxy answer from the device copy

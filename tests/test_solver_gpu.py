@@ -152,6 +152,44 @@ def test_incremental_pca_left_factor_stays_on_the_device(gpu_backend, ref):
     assert ef <= 0.1 + 1e-3
 
 
+def test_incremental_pca_chunk_prefetch(gpu_backend, ref):
+    """lra.icompute with the next chunk uploaded in the background (vectors._ChunkPrefetch, active inside compat's
+    hooked icompute): every chunk after the first is adopted from the prefetch, results identical to blocking uploads."""
+    from raleigh.interfaces.pca import pca
+    from raleigh.examples.pca.generate_matrix import generate
+    from raleigh_b200 import vectors
+    np.random.seed(1)
+    A, sigma, u, v = generate(1000, 400, 200, pca=True)
+    pf = vectors._chunk_prefetch
+    saved_min = vectors.CHUNK_PREFETCH_MIN_BYTES
+    orig_claim, orig_start = pf.claim, pf.start_next
+    hits = []
+
+    def counting_claim(a, ld_bytes):
+        got = orig_claim(a, ld_bytes)
+        hits.append(got is not None)
+        return got
+
+    try:
+        vectors.CHUNK_PREFETCH_MIN_BYTES = 0
+        pf.claim = counting_claim
+        np.random.seed(7)
+        r1 = pca(A, batch_size=300, tol=0.1, arch='gpu!', opt=ref.Options())
+        assert hits == [False, True, True, True], hits          # 300 + 300 + 300 + 100 rows
+        pf.start_next = lambda a, ld_bytes: None
+        del hits[:]
+        np.random.seed(7)
+        r0 = pca(A, batch_size=300, tol=0.1, arch='gpu!', opt=ref.Options())
+        assert not any(hits)
+    finally:
+        vectors.CHUNK_PREFETCH_MIN_BYTES = saved_min
+        pf.claim, pf.start_next = orig_claim, orig_start
+        pf.drop()
+    for a, b in zip(r0, r1):
+        assert np.array_equal(a, b)
+    assert not vectors.CHUNK_PREFETCH
+
+
 def test_pca_doctest(gpu_backend, ref):
     """interfaces/pca.py:92-133 known answers, arch='gpu!'."""
     g = np.load(os.path.join(GOLDEN, 'pca.npz'))
