@@ -372,6 +372,28 @@ def hook_device_lra_update():
         cls.icompute = icompute
 
 
+def hook_device_operator_svd():
+    """_OperatorSVD.apply (partial_svd.py:258-291) -> opsvd.apply: the rank-one mean-shift corrections keep their
+    coefficients on the device, no pipeline drain per operator application."""
+    try:
+        import raleigh.interfaces.partial_svd as rpsvd
+    except ImportError:
+        return
+    cls = rpsvd._OperatorSVD
+    if getattr(cls, '_reference_apply', None) is not None:
+        return
+    cls._reference_apply = cls.apply
+
+    def apply(self, x, y):
+        if DEVICE_SOLVER:
+            from . import opsvd
+            if opsvd.supported(self, x, y):
+                return opsvd.apply(self, x, y)
+        return cls._reference_apply(self, x, y)
+
+    cls.apply = apply
+
+
 def install(reference_path=None, sparse=True, dense=True):
     """Alias the backend into `raleigh.algebra`; returns the `raleigh` package.
     Raises ImportError if the reference package cannot be found."""
@@ -402,4 +424,5 @@ def install(reference_path=None, sparse=True, dense=True):
     hook_device_solver()
     hook_device_finalize_svd()
     hook_device_lra_update()
+    hook_device_operator_svd()
     return raleigh
