@@ -26,7 +26,7 @@ extern int64_t g_launches;          // kernels launched by this library (api.cu)
 //  CHOL_GLOBAL: 1 = pivoted Cholesky always in global memory (the shared-memory split is the default);
 //  EIG_LEGACY: 1 = always use the cooperative-grid two-sided Jacobi kernel (small.cu) instead of the cluster kernel
 enum Knob { KNOB_GRAM_TMA = 0, KNOB_SPMM_CARVEOUT = 1, KNOB_SPMM_WPS = 2, KNOB_SPMM_PREFETCH = 3, KNOB_GRAM_INTERLEAVE = 4, KNOB_GRAM_WAVES = 5, KNOB_GRAM_CHUNK_MAJOR = 6, KNOB_COPY_DIRECT = 7, KNOB_GEMM_INSPLIT = 8,
-            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_GEMM_SKINNY = 12, KNOB_CHOL_NOEST = 13, KNOB_EIG_GRID_FLAT = 14, KNOB_EIG_RING_DEBUG = 15, KNOB_COUNT = 16 };
+            KNOB_EIG_LEGACY = 9, KNOB_CHOL_GLOBAL = 10, KNOB_BLOCK_TC = 11, KNOB_GEMM_SKINNY = 12, KNOB_CHOL_NOEST = 13, KNOB_EIG_GRID_FLAT = 14, KNOB_EIG_RING_DEBUG = 15, KNOB_GEMM_DMMA = 16, KNOB_COUNT = 24 };
 extern int g_knob[KNOB_COUNT];
 int sm_count();                     // cached cudaDevAttrMultiProcessorCount
 

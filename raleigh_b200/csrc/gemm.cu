@@ -16,6 +16,9 @@ int gemm_simt(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, i
 template <typename T>
 int gemm_skinny(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
                 int64_t k, int transp, double alpha, double beta, cudaStream_t st);
+bool gemm_dmma_supported(const void* a, int64_t lda, const void* x, int64_t ldx, const void* y, int64_t ldy);
+int gemm_dmma(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
+              int64_t k, int transp, double alpha, double beta, cudaStream_t st);
 }
 
 using namespace rl;
@@ -34,9 +37,13 @@ int rl_dense_apply(int dtype, const void* a, int64_t lda, int64_t M, int64_t N, 
     if (dtype == RL_F32)
         return skinny ? gemm_skinny<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st)
                       : gemm_simt<float>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
-    if (dtype == RL_F64)
-        return skinny ? gemm_skinny<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st)
-                      : gemm_simt<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+    if (dtype == RL_F64) {
+        if (skinny) return gemm_skinny<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+        // FP64 tensor pipe (gemm_dmma.cu) whenever the operands allow 16-byte accesses; knob GEMM_DMMA = -1: FMA pipe
+        if (g_knob[KNOB_GEMM_DMMA] >= 0 && y != x && gemm_dmma_supported(a, lda, x, ldx, y, ldy))
+            return gemm_dmma(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+        return gemm_simt<double>(a, lda, M, N, x, ldx, y, ldy, k, transp, alpha, beta, st);
+    }
     return RL_E_DTYPE;
 }
 

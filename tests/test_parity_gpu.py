@@ -163,6 +163,36 @@ def test_dense_apply(gpu_backend, dtype, M, N, k):
     close(Y.data(), K.dense_apply(exp, x), dtype, fac)
 
 
+@pytest.mark.parametrize('M,N,k', [(5, 7, 9), (64, 64, 16), (130, 258, 17), (1000, 334, 128), (257, 1024, 130), (48, 20000, 33),
+                                   (3001, 66, 200)])
+def test_dense_apply_fp64_tensor_pipe(gpu_backend, M, N, k):
+    """fp64 Matrix.apply with more than 8 vectors runs on the FP64 tensor pipe (csrc/gemm_dmma.cu: cp.async ring,
+    m8n8k4 DMMA); both orientations, ragged edges in all three dimensions, alpha/beta, against NumPy and against the
+    FMA-pipe kernel (knob 16 = -1)."""
+    from raleigh_b200._lib import lib
+    rng = np.random.RandomState(M + N + k)
+    a = rng.randn(M, N)
+    x = rng.randn(k, N)
+    A = gpu_backend.Matrix(a.copy())
+    X, Y = gpu_backend.Vectors(x.copy()), gpu_backend.Vectors(M, k, np.float64)
+    A.apply(X, Y)
+    y = x @ a.T
+    assert np.max(np.abs(Y.data() - y)) <= 1e-13 * np.max(np.abs(y)) * np.sqrt(N)
+    Z = gpu_backend.Vectors(N, k, np.float64)
+    A.apply(Y, Z, transp=True)
+    z = y @ a
+    assert np.max(np.abs(Z.data() - z)) <= 1e-13 * np.max(np.abs(z)) * np.sqrt(M)
+    lib.rl_debug_set_knob(16, -1)
+    try:
+        Y2, Z2 = gpu_backend.Vectors(M, k, np.float64), gpu_backend.Vectors(N, k, np.float64)
+        A.apply(X, Y2)
+        A.apply(Y, Z2, transp=True)
+    finally:
+        lib.rl_debug_set_knob(16, 0)
+    assert np.max(np.abs(Y2.data() - Y.data())) <= 1e-13 * np.max(np.abs(y)) * np.sqrt(N)
+    assert np.max(np.abs(Z2.data() - Z.data())) <= 1e-13 * np.max(np.abs(z)) * np.sqrt(M)
+
+
 @pytest.mark.parametrize('dtype', [np.float64, np.float32])
 def test_data_matrix_as_vectors_paths(gpu_backend, dtype):
     """lra.update shapes: thousands of short vectors aliasing a data chunk
