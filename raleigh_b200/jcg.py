@@ -381,6 +381,12 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         eng.gram(BY, Y, eng.GB.sub(nx, nx, ny, ny))
         eng.mirror_upper(eng.GB, nx, ny)
         eng.piv_chol(eng.GB, nxy, nx, chol_eps)
+        # The operator is applied to ALL candidate directions before the host learns which of them survive: the
+        # device works through A Y while the host waits for the pivot packet, instead of idling until the host has
+        # read it and launched the gather.  Column j of A Y depends on column j of Y only, so gathering A Y by the
+        # pivot order afterwards gives the same block as applying A to the gathered Y (solver.py:1424-1440).
+        AYf = pool.take(ny)
+        opA.apply(BY if pro else Y, AYf)
         dropped, ind = eng.fetch_chol(nxy)
         if dropped > 0 and verb > 0:
             print('dropped %d search directions out of %d' % (dropped, ny))
@@ -402,9 +408,12 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         else:
             BY = Y
 
-        # A-Gram matrix of (X, Y) (solver.py:1437-1454)
         AY = pool.take(ny)
-        opA.apply(BY if pro else Y, AY)
+        AYf.select(ny + dropped)
+        eng.gather(AYf, ind[nx:nxy] - nx, AY)
+        pool.give(AYf)
+
+        # A-Gram matrix of (X, Y) (solver.py:1437-1454)
         if nx > 0:
             eng.copy_small(eng.XAX.sub(x0, x0, nx, nx), eng.GA.sub(0, 0, nx, nx))
             eng.gram(AY, BX if pro else X, eng.GA.sub(0, nx, nx, ny))
@@ -423,9 +432,6 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
 
         # Rayleigh-Ritz (solver.py:1456-1493, 1589-1607), all on the device
         eng.rayleigh_ritz(nx, ny, lay.leftX, lay.rightX, new.leftX, new.rightX)
-        change, predicted = eng.fetch_estimates(nx)
-        hist.push_record(ix, nx, predicted, change)
-        hist.shift(lay.left_block, new.left_block, shift_left, shift_right)
 
         # new X, Z and their images (solver.py:1609-1656); buffers rotate, nothing is copied back
         nxn = new.nx
@@ -456,6 +462,11 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         else:
             BX = Xn
         X, AX = Xn, AXn
+        # the change estimates of the Ritz step are host bookkeeping only: read them AFTER the block updates are
+        # queued (coefficients and layout are already on the device / known), so the wait overlaps those kernels
+        change, predicted = eng.fetch_estimates(nx)
+        hist.push_record(ix, nx, predicted, change)
+        hist.shift(lay.left_block, new.left_block, shift_left, shift_right)
         nz = nz_new
         lay = new
         solver.iteration += 1
