@@ -249,6 +249,7 @@ class NumpyEngine:
         self.ZAY, self.ZBY, self.Beta, self.T1 = z(m, m), z(m, m), z(m, m), z(m, m)
         self.CX, self.CZ = z(M, m), z(M, M)
         self.v_s2, self.v_t2, self.v_lmd = z(1, M), z(1, M), z(1, M)
+        self.v_y2 = z(1, M)
         self.lmdx, self.lmdz = np.zeros(M), np.zeros(M)
         self.stats = np.zeros(4)
         self.Gc = self.TC = self.QC = None
@@ -327,7 +328,7 @@ class NumpyEngine:
         lmd = self.v_lmd.a[0, :ny]
         num = self.ZAY.a[:nz, :ny] - self.ZBY.a[:nz, :ny] * lmd[None, :]
         den = self.lmdz[:nz, None] - lmd[None, :]
-        sy = np.sqrt(np.abs(self.v_s2.a[0, :ny]))
+        sy = np.sqrt(np.abs(self.v_y2.a[0, :ny]))
         sz = np.sqrt(np.abs(self.v_t2.a[0, :nz]))
         with np.errstate(divide='ignore', invalid='ignore'):
             ratio = sy[None, :] / sz[:, None]

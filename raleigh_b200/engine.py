@@ -72,6 +72,7 @@ class DeviceEngine:
         self.v_lmd = DSmall(ritz + 8 * 8, M, 1, M)
         self.v_s2 = DSmall(ritz + (8 + M) * 8, M, 1, M)
         self.v_t2 = ar.matrix(1, M)
+        self.v_y2 = ar.matrix(1, M)          # squared norms of the search directions (conjugation)
         self._chol_ptr = ar.take((8 + M) * 4)
         self._est_ptr = ar.take(2 * M * 8)
         self._lmdx = ar.take(M * 8)
@@ -204,7 +205,7 @@ class DeviceEngine:
 
     def conjugation(self, nz, ny):
         check(lib.rl_rr_conjugation(self.ZAY.ptr, self.ZBY.ptr, self.Beta.ptr, self.ZAY.ld, nz, ny, self.v_lmd.ptr,
-                                    self._lmdz, self.v_s2.ptr, self.v_t2.ptr, dev.stream()))
+                                    self._lmdz, self.v_y2.ptr, self.v_t2.ptr, dev.stream()))
 
     def piv_chol(self, G, n, k, eps):
         check(lib.rl_rr_piv_chol(G.ptr, self._A0.ptr, G.ld, n, k, float(eps), self._chol_ptr + 32, self._chol_ptr,

@@ -240,6 +240,10 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         W = pool.take(nx)
         BW = pool.take(nx) if pro else None                  # product form: B-image of the residuals
         _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB if pro else None)
+        # Search directions for the whole (old) window -- preconditioning and conjugation to the previous directions
+        # (solver.py:1315-1351) -- depend on nothing the host is about to decide: they are queued BEFORE the host
+        # reads the Ritz packet, so the device works on them while the host does its convergence bookkeeping.
+        Y = _directions(eng, pool, opP, pro, hasB, W, BW, Z, AZ, BZ, nz, nx)
         new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
         if verb > 2:
             print('Ritz values error: %.1e' % rv_err)
@@ -255,6 +259,9 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
             eng.ritz_check(nx)
             W.select(nx)
             _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB if pro else None)
+            if Y is not W:
+                pool.give(Y)
+            Y = _directions(eng, pool, opP, pro, hasB, W, BW, None, None, None, 0, nx)      # nz = 0: no conjugation
             new_lmd, res2, rv_err, rv_no = eng.fetch_ritz(nx)
 
         hist.record_ritz_values(ix, new_lmd)
@@ -315,33 +322,11 @@ def solve(solver, eigenvectors, options, which, extra, init, engine):
         AX.select(nx, x0)
         BX.select(nx, x0)
 
-        # search directions: preconditioned residuals (solver.py:1315-1319)
-        if opP is None or pro:               # product form: no preconditioning step (solver.py:1315)
-            Y = W
-        else:
-            Y = pool.take(ny)
-            W.select(ny)
-            opP.apply(W, Y)
+        # search directions: computed above, one per OLD iterate (solver.py:1315-1351)
+        if Y is not W:
             pool.give(W)
         W = None
         Y.select(ny)
-
-        # conjugation to the previous directions (solver.py:1321-1351)
-        if nz > 0:
-            Z.select(nz)
-            AZ.select(nz)
-            if hasB:
-                BZ.select(nz)
-            if pro:
-                BW.select(ny)
-            eng.gram(BW if pro else Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
-            eng.gram(Y, BZ if hasB else Z, eng.ZBY.sub(0, 0, nz, ny))
-            eng.dots(Y, Y, eng.v_s2)
-            eng.dots(Z, Z, eng.v_t2)
-            eng.conjugation(nz, ny)               # uses the Ritz values of the OLD window, v_lmd[0:ny]
-            eng.update(Y, Z, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
-            if pro:
-                eng.update(BW, BZ, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
 
         # orthogonalise to X and to the locked vectors, normalise (solver.py:1360-1381)
         if pro:
@@ -586,6 +571,35 @@ def _residuals(eng, W, BW, X, BX, AX, Xc, BXc, nc, nx, gen, opB_pro):
         eng.dots(BW, W, eng.v_s2)
     else:
         eng.dots(W, W, eng.v_s2)
+
+
+def _directions(eng, pool, opP, pro, hasB, W, BW, Z, AZ, BZ, nz, ny):
+    """Y = T W (or W itself), conjugated to the previous directions Z: Y -= Z Beta with Beta from
+    (Z^T A Y - Z^T B Y lmd) / (lmdz - lmd) (solver.py:1315-1351; rl_rr_conjugation).  Product form: no
+    preconditioner, A-products taken with the image block BW, which is updated alongside."""
+    if opP is None or pro:
+        Y = W
+    else:
+        Y = pool.take(ny)
+        W.select(ny)
+        opP.apply(W, Y)
+    Y.select(ny)
+    if nz > 0:
+        Z.select(nz)
+        AZ.select(nz)
+        if hasB:
+            BZ.select(nz)
+        if pro:
+            BW.select(ny)
+        eng.gram(BW if pro else Y, AZ, eng.ZAY.sub(0, 0, nz, ny))
+        eng.gram(Y, BZ if hasB else Z, eng.ZBY.sub(0, 0, nz, ny))
+        eng.dots(Y, Y, eng.v_y2)              # not v_s2: the residual norms in the Ritz packet are still unread
+        eng.dots(Z, Z, eng.v_t2)
+        eng.conjugation(nz, ny)               # uses the Ritz values of the OLD window, v_lmd[0:ny]
+        eng.update(Y, Z, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
+        if pro:
+            eng.update(BW, BZ, eng.Beta.sub(0, 0, nz, ny), -1.0, 1.0)
+    return Y
 
 
 def _rotate(eng, pool, blocks, k, mout):
