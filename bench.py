@@ -162,47 +162,96 @@ def pca_error_gpu(a_dev, mean, trans, comps):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (two cheap queries every
+    100 ms from a thread started before the warm-up); `nvidia-smi -lms` as a fallback.  r2ai: the earlier version
+    launched the nvidia-smi process right before the timed region -- its start-up (NVML initialisation over all the
+    GPUs of the box) and its seven-field queries held driver locks during the measurement and cost the resident arm
+    15-50 ms on some boxes (device_busy_frac 0.62 with `value` above the end-to-end number)."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    PERIOD = 0.1
 
     def __init__(self, index=0):
-        self.rows = []
+        self.rows = []            # (time, sm_mhz, reasons set)
+        self.smax = None
         self.proc = None
+        self.mode = None
+        self._stop = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.mode = 'nvml'
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = 'nvidia-smi'
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                return int(vis.split(',')[index])
+            except (ValueError, IndexError):
+                pass
+        return index
+
+    def _poll_nvml(self):
+        nv = self._nv
+        names = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown', 0x8), ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap', 0x4))
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons', None)
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = int(get_reasons(self._h)) if get_reasons else 0
+                self.rows.append((time.time(), sm, {n for n, _, bit in names if mask & bit}))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1:
-                continue
-            parts = [p.strip() for p in line.split(',')]
+            parts = [p.strip() for p in line.strip().split(',')]
             try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
+                sm = float(parts[0])
+                self.smax = float(parts[1])
             except (ValueError, IndexError):
                 continue
-            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
-                                 parts[3:7]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
+            reasons = {name for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[3:7])
+                       if val.lower().startswith('active')}
+            self.rows.append((time.time(), sm, reasons))
+
+    def stop(self, t0, t1):
+        if self.mode is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml / nvidia-smi unavailable']}
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, reasons = [], set()
+        for ts, mhz, why in list(self.rows):
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(mhz)
+            reasons |= why
         sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'samples': len(sm),
-                'reasons': sorted(reasons)}
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.smax, 'samples': len(sm),
+                'reasons': sorted(reasons), 'source': self.mode}
 
 
 # --------------------------------------------------------------------------- reference CPU path
@@ -547,9 +596,9 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- resident arm ("value")
     matrix = AMatrix(a_host, arch='gpu!')
+    sampler = ClockSampler(local_rank) if rank == 0 else None       # started BEFORE the warm-up: see its docstring
     for _ in range(args.warmup):
         lra = solve_resident(matrix)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     profile.reset()
     profile.enable(True)
     launches0 = cuda.launch_count()
