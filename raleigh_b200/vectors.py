@@ -609,11 +609,14 @@ class Vectors:
             return numpy.ndarray((m, self._ng), dtype=self._dtype)
         if LAZY_DATA_MIN_BYTES is not None and m * self._n * self._w >= LAZY_DATA_MIN_BYTES:
             return DeviceData(self)                    # inside compat's hooked lra.update only
-        local = dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
         if self._shard is None:
-            return local
+            return dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
         ctx = self._shard[0]
-        return ctx.allgather_columns(local, ctx.allgather_counts(self._n))
+        counts = ctx.allgather_counts(self._n)
+        if ctx.on_device:
+            return ctx.allgather_columns_device(self._wptr(), self._ld, m, self._n, self._dtype, counts)
+        local = dev.download_2d(self._wptr(), self._ld * self._w, m, self._n, self._dtype)
+        return ctx.allgather_columns(local, counts)
 
     def local_data(self):
         """The rows of the selected vectors this process owns, (nvec, nloc)."""
