@@ -310,8 +310,7 @@ class _LraNumpyProxy:
     def concatenate(self, arrays, axis=0, *args, **kwargs):
         from .vectors import DeviceData
         arrays = tuple(arrays)
-        if axis == 1 and len(arrays) == 2 and not args and not kwargs and all(isinstance(a, DeviceData) for a in arrays) \
-                and all(a._vec is not None for a in arrays):
+        if axis == 1 and len(arrays) == 2 and not args and not kwargs and all(isinstance(a, DeviceData) for a in arrays):
             return arrays[0].concatenate(arrays[1])
         arrays = tuple(self._np.asarray(a) if isinstance(a, DeviceData) else a for a in arrays)
         return self._np.concatenate(arrays, axis, *args, **kwargs)
