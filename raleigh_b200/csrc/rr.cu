@@ -18,6 +18,10 @@
 #include "common.cuh"
 
 namespace rl {
+bool gemm_dmma_supported(const void* a, int64_t lda, const void* x, int64_t ldx, const void* y, int64_t ldy);
+int gemm_dmma(const void* a, int64_t lda, int64_t M, int64_t N, const void* x, int64_t ldx, void* y, int64_t ldy,
+              int64_t k, int transp, double alpha, double beta, cudaStream_t st);
+
 
 // tcgen05 / TMEM / TMA GEMM of gemm_tc.cu (3xTF32, fp32 result)
 bool gemm_tc_supported(const void* a, int64_t lda, const void* x, int64_t ldx);
@@ -1000,6 +1004,13 @@ int rl_small_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, doubl
     dim3 grid((unsigned)((N + SG_T - 1) / SG_T), (unsigned)((M + SG_T - 1) / SG_T));
     cudaStream_t st = as_stream(stream);
     Span span(PK_SMALL, st, (1.0 * M * K + 1.0 * K * N + 2.0 * M * N) * 8, 2.0 * M * N * K);
+    // big products (the locked-vector projections late in a config-2 solve: 1000 x 1000 x 128, 0.22 ms on the FMA
+    // kernel) go to the FP64 tensor-pipe GEMM of the dense apply: C[v,o] = sum_r A[v,r] op(B)[r,o] is its
+    // "X times matrix" form with X = A
+    if (!transa && K > 0 && (double)M * N * K >= 5.0e7 && C != A && C != B && g_knob[KNOB_GEMM_DMMA] >= 0 &&
+        gemm_dmma_supported(B, ldb, A, lda, C, ldc))
+        return transb ? gemm_dmma(B, ldb, N, K, A, lda, C, ldc, M, 0, alpha, beta, st)
+                      : gemm_dmma(B, ldb, K, N, A, lda, C, ldc, M, 1, alpha, beta, st);
     if (transa && transb) small_gemm_kernel<true, true><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (transa) small_gemm_kernel<true, false><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (transb) small_gemm_kernel<false, true><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);

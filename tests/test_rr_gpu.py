@@ -376,11 +376,11 @@ def test_ritz_check_and_conjugation(rt):
     eng = E.NumpyEngine()
     z = lambda r, c: E.Small(np.zeros((r, c)))
     eng.ZAY, eng.ZBY, eng.Beta = E.Small(rng.randn(nz, ld)), E.Small(rng.randn(nz, ld)), z(nz, ld)
-    eng.v_lmd, eng.v_s2, eng.v_t2 = E.Small(rng.randn(1, ld)), E.Small(rng.rand(1, ld)), E.Small(rng.rand(1, ld))
+    eng.v_lmd, eng.v_y2, eng.v_t2 = E.Small(rng.randn(1, ld)), E.Small(rng.rand(1, ld)), E.Small(rng.rand(1, ld))
     eng.lmdz = rng.randn(ld)
     eng.ZAY.a[3, 4] = 1e9            # a coefficient the safeguard must zero
     eng.conjugation(nz, ny)
-    dz = [rt.up(a) for a in (eng.ZAY.a, eng.ZBY.a, eng.v_lmd.a, eng.lmdz, eng.v_s2.a, eng.v_t2.a)]
+    dz = [rt.up(a) for a in (eng.ZAY.a, eng.ZBY.a, eng.v_lmd.a, eng.lmdz, eng.v_y2.a, eng.v_t2.a)]
     beta = rt.zeros(nz, ld)
     rt.check(rt.lib.rl_rr_conjugation(dz[0].data_ptr(), dz[1].data_ptr(), beta.data_ptr(), ld, nz, ny, dz[2].data_ptr(),
                                       dz[3].data_ptr(), dz[4].data_ptr(), dz[5].data_ptr(), rt.st()))
