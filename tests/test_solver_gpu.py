@@ -190,6 +190,43 @@ def test_incremental_pca_chunk_prefetch(gpu_backend, ref):
     assert not vectors.CHUNK_PREFETCH
 
 
+def test_incremental_pca_from_npy_memory_map(gpu_backend, ref, tmp_path):
+    """examples/pca/incremental_pca.py:43 streams `numpy.load(path, mmap_mode='r')` through pca(batch_size=...):
+    chunks of the memory map are uploaded (and prefetched) like chunks of an array; same result."""
+    from raleigh.interfaces.pca import pca
+    from raleigh.examples.pca.generate_matrix import generate
+    from raleigh_b200 import vectors, io
+    np.random.seed(1)
+    A, sigma, u, v = generate(900, 400, 200, pca=True)
+    path = str(tmp_path / 'data.npy')
+    np.save(path, A)
+    data = io.open_npy(path)
+    pf = vectors._chunk_prefetch
+    saved_min = vectors.CHUNK_PREFETCH_MIN_BYTES
+    orig_claim = pf.claim
+    hits = []
+
+    def counting_claim(a, ld_bytes):
+        got = orig_claim(a, ld_bytes)
+        hits.append(got is not None)
+        return got
+
+    try:
+        vectors.CHUNK_PREFETCH_MIN_BYTES = 0
+        pf.claim = counting_claim
+        np.random.seed(7)
+        r1 = pca(data, batch_size=300, tol=0.1, arch='gpu!', opt=ref.Options())
+        assert hits == [False, True, True], hits
+        np.random.seed(7)
+        r0 = pca(A, batch_size=300, tol=0.1, arch='gpu!', opt=ref.Options())
+    finally:
+        vectors.CHUNK_PREFETCH_MIN_BYTES = saved_min
+        pf.claim = orig_claim
+        pf.drop()
+    for a, b in zip(r0, r1):
+        assert np.array_equal(a, b)
+
+
 def test_pca_doctest(gpu_backend, ref):
     """interfaces/pca.py:92-133 known answers, arch='gpu!'."""
     g = np.load(os.path.join(GOLDEN, 'pca.npz'))
