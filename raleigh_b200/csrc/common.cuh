@@ -17,9 +17,14 @@ extern int64_t g_launches;          // kernels launched by this library (api.cu)
 //  SPMM_CARVEOUT: shared-memory carve-out in percent; SPMM_WPS: 16 = 127-register budget + 4-entry batches,
 //            24 = 80 registers + 2-entry batches; SPMM_PREFETCH: -1 off, bit 0 largest-column lines,
 //            bit 1 CSR entries of the run one resident window ahead, bit 2 X lines shifted by that window;
-//  (knobs 6, 7: the r1 band-window SpMM experiment, measured 0.60 vs 0.33 ms on the 128^3 stencil in r2a and removed;
-//   profiles/r2a_sweep_spmm_window.jsonl)
-//  GEMM_INSPLIT: 1 = experimental in-kernel lo split of the tcgen05 dense apply (gemm_tc.cu)
+//  (knobs 6, 7 belonged to the r1 band-window SpMM experiment, measured 0.60 vs 0.33 ms on the 128^3 stencil in r2a
+//   and removed, profiles/r2a_sweep_spmm_window.jsonl; the numbers were reused:)
+//  GRAM_CHUNK_MAJOR: 1 = multi-tile Gram products keep the chunk-major 3-D grid (default: tile-major 1-D grid);
+//  COPY_DIRECT: 1 = big pageable host<->device copies go straight to cudaMemcpy (default: pinned staging + threads);
+//  GEMM_INSPLIT: in-kernel lo split of the tcgen05 dense apply (gemm_tc.cu), the default since r2
+//  EIG_GRID_FLAT: 1 = orders 321..1024 on the flat one-grid-barrier-per-round Jacobi kernel (default: ring kernel);
+//  EIG_RING_DEBUG: timing experiments on the ring kernel (bit 0: no rotations, bit 1: no block movement; six sweeps);
+//  GEMM_DMMA: -1 = fp64 dense apply / big small-matrix products on the FMA-pipe kernels instead of gemm_dmma.cu;
 //  CHOL_NOEST: 1 = (measurements only) pivoted Cholesky without the condition estimates of the drop rule;
 //  GEMM_SKINNY: -1 = dense applies with k <= 8 vectors stay on the tiled FMA kernel (gemm_simt.cu);
 //  BLOCK_TC: -1 = fp32 Gram / block update of the device-resident driver never on the tensor cores;
