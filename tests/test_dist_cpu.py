@@ -66,6 +66,37 @@ def _worker(rank, world, port, out):
         Aloc = sp.csr_matrix((slab.data, plan.local_indices, plan.indptr), shape=(nl, nl + plan.nhalo))
         yloc = (Aloc @ xext.T).T
         assert np.allclose(yloc, (A @ xg.T).T[:, r0:r0 + nl], atol=1e-9)
+    # append(axis=1) of two row-sharded blocks (vectors.py: append) registers the joined dimension process-major:
+    # rows of process 0 of both blocks, then process 1, ... -- a contiguous partition again, and data() of the
+    # joined block is the process-major concatenation
+    n1 = 400
+    r1, l1 = ctx.register_even(n1)
+    ctx.register(n + n1, row0 + r1, nloc + l1)
+    joined_counts = ctx.allgather_counts(nloc + l1)
+    assert sum(joined_counts) == n + n1 and sum(joined_counts[:rank]) == row0 + r1
+    xb = rng.randn(5, n1)
+    mine = np.hstack((xl, xb[:, r1:r1 + l1]))
+    gathered = ctx.allgather_columns(mine, joined_counts)
+    expect = np.hstack([np.hstack((x[:, a:a + b], xb[:, c:c + d]))
+                        for (a, b), (c, d) in ((dist.partition(n, world, r), dist.partition(n1, world, r)) for r in range(world))])
+    assert np.array_equal(gathered, expect)
+    # Matrix Market file -> per-process row slab -> halo plan (io.read_matrix_market; nobody holds the whole matrix)
+    import scipy.io
+    from raleigh_b200 import io as rio
+    path = os.path.join(out['tmp'], 'lap.mtx')
+    if rank == 0:
+        scipy.io.mmwrite(path, sp.triu(L).tocoo(), symmetry='general')     # upper triangle on disk ...
+        with open(path) as f:
+            text = f.read().replace('general', 'symmetric', 1)             # ... declared symmetric
+        with open(path, 'w') as f:
+            f.write(text)
+    tdist.barrier()
+    ng = L.shape[0]
+    r0, nl = dist.partition(ng, world, rank)
+    slab = rio.read_matrix_market(path, r0, nl, block_lines=50)
+    assert abs(slab - L[r0:r0 + nl]).max() == 0.0
+    plan = dist.HaloPlan(ctx, slab.indptr, slab.indices, r0, nl, ng)
+    assert sum(plan.recv_counts) == plan.nhalo
     out[rank] = 1
     tdist.barrier()
     tdist.destroy_process_group()
@@ -84,6 +115,8 @@ def test_shard_context_gloo_world2():
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
+    import tempfile
+    out['tmp'] = tempfile.mkdtemp(prefix='rl_dist_')
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-    assert sorted(out.keys()) == [0, 1]
+    assert sorted(k for k in out.keys() if k != 'tmp') == [0, 1]
